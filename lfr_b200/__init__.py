@@ -1,0 +1,9 @@
+"""Import shim: `import lfr_b200` -> the package in ../local-feature-refinement_b200/
+(a hyphen cannot appear in a Python module name)."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                      "local-feature-refinement_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))

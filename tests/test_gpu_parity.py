@@ -1,0 +1,109 @@
+"""GPU parity: the CUDA path (through the C ABI, csrc/liblfr_b200.so) against
+the CPU oracle on identical inputs.
+
+Tolerance: BASELINE.json north_star asks for keypoint displacements within
+1e-4 px of the reference solve; 1 solver unit = 16 px
+(reconstruction-scripts/colmap_utils.py:135-136), so 6.25e-6 units.  The
+trajectory (per-component LM iteration count and termination reason) must be
+identical as well.
+"""
+import numpy as np
+import pytest
+
+from conftest import get_problem
+
+TOL_UNITS = 1e-4 / 16.0   # 1e-4 px
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(b200, oracle, p, **opts):
+    pos_g, st_g = b200.solve(p, b200.default_options(**opts))
+    pos_o, st_o = oracle.solve(p, oracle.default_options(n_threads=8, **opts))
+    err = np.abs(pos_g - pos_o).max() if pos_g.size else 0.0
+    assert err <= TOL_UNITS, "max |dx| = %.3e units (%.3e px)" % (err, err * 16)
+    np.testing.assert_array_equal(st_g["termination"], st_o["termination"])
+    np.testing.assert_array_equal(st_g["iterations"], st_o["iterations"])
+    np.testing.assert_allclose(st_g["initial_cost"], st_o["initial_cost"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(st_g["final_cost"], st_o["final_cost"], rtol=1e-8, atol=1e-14)
+    assert st_g["total_iterations"] == st_o["total_iterations"]
+    assert st_g["n_solved"] == st_o["n_solved"]
+    return err, st_g
+
+
+def test_edge_eval_matches_oracle(b200, oracle):
+    """K1: residual, Jacobian and robust weights per edge (cost.cc:13-48,78-90)."""
+    from lfr_b200 import EDGE_DTYPE
+    rng = np.random.default_rng(5)
+    n = 20000
+    e = np.zeros(n, dtype=EDGE_DTYPE)
+    e["flow"] = rng.uniform(-0.5, 0.5, size=(n, 18)).astype(np.float32)
+    e["sim"] = rng.uniform(0.5, 1.0, size=n).astype(np.float32)
+    kind = rng.integers(1, 3, size=n).astype(np.uint8)
+    xs = rng.uniform(-0.8, 0.8, size=(n, 2))          # beyond +-0.5 => clamped branch
+    xs[:100] = np.sign(xs[:100]) * 0.5                 # exactly on the clamp boundary
+    xd = rng.uniform(-1, 1, size=(n, 2))
+    # small residuals so the Tukey inlier branch is exercised too
+    e["flow"][: n // 2] *= 0.05
+    xd[: n // 2] = xs[: n // 2] + rng.normal(0, 0.02, size=(n // 2, 2))
+    rg, jg, rhog = b200.edge_eval(e, kind, xs, xd)
+    ro, jo, rhoo = oracle.edge_eval(e, kind, xs, xd)
+    np.testing.assert_allclose(rg, ro, rtol=0, atol=4e-16 * 4)
+    np.testing.assert_allclose(jg, jo, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(rhog[:, :2], rhoo[:, :2], rtol=1e-13, atol=1e-18)
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3"])
+def test_solve_matches_oracle(b200, oracle, cfg):
+    """BASELINE.json configs[0..2] at full size."""
+    _, p = get_problem(cfg)
+    err, st = _compare(b200, oracle, p)
+    print(cfg, "max err %.3e units" % err, "iters", st["total_iterations"], "kernel ms", st["kernel_ms"])
+
+
+def test_solve_tukey_variant_2(b200, oracle):
+    _, p = get_problem("cfg1")
+    _compare(b200, oracle, p, tukey_variant=2)
+
+
+def test_solve_nonzero_start_and_bounds(b200, oracle):
+    """Start points outside the box are projected at iteration 0 (A.6)."""
+    _, p = get_problem("cfg1")
+    rng = np.random.default_rng(3)
+    init = rng.uniform(-1.5, 1.5, size=(p.graph.n_nodes, 2))
+    pos_g, st_g = b200.solve(p, positions=init)
+    pos_o, st_o = oracle.solve(p, oracle.default_options(n_threads=1), positions=init)
+    assert np.abs(pos_g - pos_o).max() <= TOL_UNITS
+    np.testing.assert_array_equal(st_g["iterations"], st_o["iterations"])
+
+
+def test_line_search_contraction_path(b200, oracle):
+    """Large, inconsistent flows force Armijo contractions (cubic and, on the
+    second contraction, quintic interpolation)."""
+    from lfr_b200 import synth, build_problem
+    ms = synth.generate("cfg1", seed=77)
+    rng = np.random.default_rng(11)
+    ms.disp1[:] = rng.uniform(-1.2, 1.2, size=ms.disp1.shape).astype(np.float32)
+    ms.disp2[:] = rng.uniform(-1.2, 1.2, size=ms.disp2.shape).astype(np.float32)
+    p = build_problem(ms)
+    pos_g, st_g = b200.solve(p)
+    pos_o, st_o = oracle.solve(p, oracle.default_options(n_threads=1))
+    assert st_o["total_line_search_steps"] > 0
+    assert st_g["total_line_search_steps"] == st_o["total_line_search_steps"]
+    assert np.abs(pos_g - pos_o).max() <= TOL_UNITS
+    np.testing.assert_array_equal(st_g["iterations"], st_o["iterations"])
+
+
+def test_plan_resolve_is_deterministic(b200):
+    """Row-owned sums, no atomics: re-running the plan is bit-identical."""
+    from lfr_b200.capi import Plan
+    _, p = get_problem("cfg2")
+    plan = Plan(b200, p)
+    plan.solve()
+    a, st = plan.download()
+    plan.solve()
+    b, _ = plan.download()
+    assert np.array_equal(a, b)
+    alg, one = plan.traffic()
+    assert alg >= one > 0
+    plan.close()
