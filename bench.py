@@ -1,0 +1,331 @@
+#!/usr/bin/env python3
+"""bench.py — tracks-refined/s of the multi-view refinement solve on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+
+A step = one complete solve of the workload's match graph (every component,
+LM to termination).  At N=1 the workload is BASELINE.json configs[1]
+(Fountain-scale synthetic: 11 images x 3000 keypoints, exhaustive pairs).  For
+N>1 (torchrun, one rank per GPU) every rank solves its own Fountain-scale scene
+(weak scaling: independent components, no data-path collective — SURVEY 8e);
+`value` = tracks of all ranks / max-over-ranks time.
+
+  value     device-resident plan (inputs already in HBM), CUDA events per step on
+            the launching stream, L2 flushed between steps (untimed)
+  e2e       the same solve through the C-ABI call lfr_solve() with pinned HOST
+            buffers: host->device copies, kernels and device->host results inside
+            the timed region
+  roofline  algorithmic bytes (sum_c iters_c (80 E_c + 36 N_c)) / kernel time
+            against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (oracle/, a restatement of the reference's
+            Ceres solve — the reference itself cannot be built here) on the host cores
+
+--impl reference times that CPU oracle as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "tracks_refined_per_s"
+UNIT = "tracks/s"
+WORKLOADS = {
+    "cfg1": "cfg1 synthetic 3 images x 200 kpts, exhaustive pairs",
+    "cfg2": "cfg2 Fountain-scale synthetic: 11 images x 3000 kpts, exhaustive pairs",
+    "cfg3": "cfg3 Herzjesu-scale synthetic: 8 images x 8000 kpts, exhaustive pairs",
+    "cfg4": "cfg4 ETH3D-courtyard-scale synthetic: 38 images x 4000 kpts, sequential+loop pairs",
+    "cfg5": "cfg5 Madrid-Metropolis-scale synthetic: 1000 images x 2000 kpts, ring+random pairs",
+}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def ncu_traffic():
+    """DRAM bytes per step of the solve kernels from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get("dram_bytes_per_step")
+    except Exception:
+        return None
+
+
+def build_workload(name, seed=None):
+    from lfr_b200 import build_problem, refined_track_count, synth
+    ms = synth.generate(name, seed=seed)
+    p = build_problem(ms)
+    return p, refined_track_count(p)
+
+
+def workload_config(name, p, n_tracks, extra=None):
+    sizes = np.diff(p.comp_ptr.astype(np.int64))
+    cfg = {"workload": WORKLOADS.get(name, name), "nodes": int(p.graph.n_nodes),
+           "directed_edges": int(p.graph.n_edges), "tracks": int(p.info.get("n_tracks", 0)),
+           "tracks_refined": int(n_tracks), "components_solved": int((sizes > 1).sum()),
+           "max_component_nodes": int(sizes.max()) if sizes.size else 0}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pinned_problem(lib, p):
+    """Marshal the problem into pinned host buffers (what a host application
+    hands to lfr_solve)."""
+    import ctypes as C
+    import torch
+    from lfr_b200.capi import LfrProblem
+    s, arrays = lib.marshal(p)
+    pinned = {}
+    for k, a in arrays.items():
+        raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        t = torch.empty(max(raw.size, 1), dtype=torch.uint8).pin_memory()
+        t.numpy()[:raw.size] = raw
+        pinned[k] = t
+    s2 = LfrProblem(n_nodes=s.n_nodes, n_components=s.n_components, n_edges=s.n_edges,
+                    **{k: t.data_ptr() for k, t in pinned.items()})
+    N = p.graph.n_nodes
+    pos = torch.zeros(max(2 * N, 1), dtype=torch.float64).pin_memory()
+    h2d = sum(int(np.ascontiguousarray(a).nbytes) for a in arrays.values()) + 16 * N
+    return s2, pinned, pos, h2d
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU solve (solve.cc:614-635 on a thread
+    pool), i.e. the restated oracle — the Ceres/COLMAP build is unavailable here."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_util import load_oracle
+    orc = load_oracle()
+    cores = os.cpu_count() or 1
+    p, n_tracks = build_workload(args.workload)
+    o = orc.default_options(n_threads=cores)
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < max(args.warmup, 3) or time.perf_counter() - t_w < 1.5:   # host threads / clocks settle
+        orc.solve(p, o)
+        n_w += 1
+    t = []
+    iters = 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        _, st = orc.solve(p, o)
+        t.append(time.perf_counter() - t0)
+        iters = st["total_iterations"]
+    ms = 1e3 * float(np.mean(t))
+    value = n_tracks / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, p, n_tracks),
+            "lm_iters_per_s": iters / (ms / 1e3),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "whole workload, %d steps; Ceres-1.14-semantics CPU oracle "
+                                       "(oracle/lfr_oracle.cc, -O2) — the reference's Ceres/COLMAP "
+                                       "build is unavailable in this image" % args.steps},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from lfr_b200.capi import Plan, load_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the solve has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = load_b200()
+    opts = lib.default_options(device=local)
+    # weak scaling: rank r solves its own scene (seed offset), same shape
+    from lfr_b200 import synth
+    base_seed = synth.CONFIGS[synth.ALIASES.get(args.workload, args.workload)].seed
+    p, n_tracks = build_workload(args.workload, seed=base_seed + 7919 * rank if world > 1 else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    plan = Plan(lib, p, opts)
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        plan.solve(stream)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- value: device-resident, CUDA events per step ---------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        plan.solve(stream)
+        b.record()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    ms_per_step = float(np.mean(step_ms))
+    _, st = plan.download(stream)
+    alg_bytes, one_pass = plan.traffic(stream)
+    launches = plan.num_launches()
+    # ---- e2e: C-ABI call with pinned host buffers ------------------------------------------
+    s2, keep, pos_pinned, h2d = pinned_problem(lib, p)
+    stt, bufs = lib.make_stats(p.n_components)
+    d2h = 16 * p.graph.n_nodes + 8 * p.n_components
+    e2e_t = []
+    for i in range(args.warmup + args.steps):
+        pos_pinned.zero_()
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        rc = lib.lib.lfr_solve(C.byref(s2), C.byref(opts), pos_pinned.data_ptr(), C.byref(stt))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        lib.check(rc, "lfr_solve")
+        if i >= args.warmup:
+            e2e_t.append(dt)
+    e2e_ms = 1e3 * float(np.mean(e2e_t))
+    clocks = sampler.stop() if sampler else None
+    # ---- reduce over ranks --------------------------------------------------------------------
+    tot_tracks, tot_iters, tot_alg = n_tracks, int(st["total_iterations"]), alg_bytes
+    if world > 1:
+        t = torch.tensor([ms_per_step, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step, e2e_ms = float(t[0]), float(t[1])
+        c = torch.tensor([n_tracks, tot_iters, alg_bytes], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        tot_tracks, tot_iters, tot_alg = int(c[0]), int(c[1]), int(c[2])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    value = tot_tracks / (ms_per_step / 1e3)
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (ms_per_step / 1e3) / 1e9     # per GPU (rank 0's solve kernels)
+    # ---- cpu baseline: oracle on the host cores, bounded sample -------------------------------
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_util import load_oracle
+    orc = load_oracle()
+    cores = os.cpu_count() or 1
+    oo = orc.default_options(n_threads=cores)
+    cpu_t = []
+    t0 = time.perf_counter()
+    while len(cpu_t) < 5 or (time.perf_counter() - t0 < 6.0 and len(cpu_t) < 300):
+        t1 = time.perf_counter()
+        orc.solve(p, oo)
+        cpu_t.append(time.perf_counter() - t1)
+    reps = len(cpu_t)
+    cpu_ms = 1e3 * float(np.median(cpu_t))   # median: robust to host-side noise at start-up
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, p, n_tracks, {
+            "per_gpu": "one scene per GPU" if world > 1 else "single scene",
+            "l2": "flushed between timed steps (256 MiB write, untimed)",
+            "lm_iterations_per_step": int(st["total_iterations"])}),
+        "lm_iters_per_s": tot_iters / (ms_per_step / 1e3),
+        "e2e": {"value": tot_tracks / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": "lfr_solve() (include/lfr.h) with pinned host buffers"},
+        "gpu_launches": int(launches * args.steps),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic(),
+                     "peak_source": "%s HBM copy bandwidth (burst)" % peak_src,
+                     "algorithmic_bytes_per_step": int(alg_bytes), "one_pass_bytes": int(one_pass),
+                     "kernel": "solve_warp_kernel (all size buckets of one step)"},
+        "cpu_baseline": {"value": n_tracks / (cpu_ms / 1e3), "unit": UNIT, "cores": cores, "kind": "port",
+                         "ms_per_step": cpu_ms,
+                         "sample": "whole workload x %d repetitions (Ceres-1.14-semantics CPU oracle, "
+                                   "oracle/lfr_oracle.cc)" % reps},
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    args = ap.parse_args()
+    args.workload = {"fountain": "cfg2", "herzjesu": "cfg3"}.get(args.workload, args.workload)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -4,6 +4,7 @@
 // computes fails with LFR_ENODEV / LFR_ECUDA when no device is usable.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,19 +20,27 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 
-#define LFR_CUDA(call)                                                                   \
-  do {                                                                                   \
-    cudaError_t err__ = (call);                                                          \
-    if (err__ != cudaSuccess) {                                                          \
-      const int code__ = (err__ == cudaErrorNoDevice || err__ == cudaErrorInsufficientDriver || \
-                          err__ == cudaErrorInvalidDevice)                               \
-                             ? LFR_ENODEV                                                \
-                             : (err__ == cudaErrorMemoryAllocation ? LFR_ENOMEM : LFR_ECUDA); \
-      return fail(code__, std::string(#call) + ": " + cudaGetErrorString(err__));        \
-    }                                                                                    \
+int cuda_code(cudaError_t e) {
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return LFR_ENODEV;
+  if (e == cudaErrorMemoryAllocation) return LFR_ENOMEM;
+  return LFR_ECUDA;
+}
+
+#define LFR_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t err__ = (call);                                                     \
+    if (err__ != cudaSuccess)                                                       \
+      return fail(cuda_code(err__), std::string(#call) + ": " + cudaGetErrorString(err__)); \
+  } while (0)
+
+#define LFR_TRY(expr)        \
+  do {                       \
+    const int rc__ = (expr); \
+    if (rc__) return rc__;   \
   } while (0)
 
 constexpr int kMaxSmemPerBlock = 227 * 1024;
+constexpr int kMaxStreams = 12;
 
 lfr::DevConsts make_consts(const lfr_options& o) {
   lfr::DevConsts K;
@@ -67,8 +76,33 @@ lfr::DevConsts make_consts(const lfr_options& o) {
   return K;
 }
 
+// Grow-only device buffer: lfr_solve() re-uses its workspace across calls, so a
+// steady stream of solves performs no cudaMalloc/cudaFree.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return LFR_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return fail(cuda_code(e), std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cap = want;
+    return LFR_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
 struct Bucket {
-  uint32_t* d_list = nullptr;
+  uint32_t offset = 0;  // into the bucket-list buffer
   uint32_t n = 0;
   int emax = 0, ncmax = 0, n2max = 0, smem_per_warp = 0, warps = 4;
 };
@@ -81,27 +115,8 @@ int validate(const lfr_problem* p) {
   if (p->n_nodes && p->row_ptr[p->n_nodes] != p->n_edges) return fail(LFR_EINVAL, "row_ptr[n_nodes] != n_edges");
   if (p->n_edges && !p->edges) return fail(LFR_EINVAL, "edges is NULL");
   if (p->n_edges >= (1ull << 32)) return fail(LFR_EUNSUPPORTED, "more than 2^32 directed edges");
-  for (uint32_t v = 0; v < p->n_nodes; ++v) {
-    if (p->row_ptr[v + 1] < p->row_ptr[v]) return fail(LFR_EINVAL, "row_ptr not monotone");
-    for (uint32_t e = p->row_ptr[v]; e < p->row_ptr[v + 1]; ++e) {
-      if (p->edges[e].dst >= p->n_nodes) return fail(LFR_EINVAL, "edge dst out of range");
-      if (p->edges[e].dst == v) return fail(LFR_EINVAL, "self edge (Ceres rejects duplicate parameter blocks)");
-    }
-  }
-  for (uint32_t c = 0; c < p->n_components; ++c)
-    if (p->comp_ptr[c + 1] < p->comp_ptr[c]) return fail(LFR_EINVAL, "comp_ptr not monotone");
-  const uint32_t tot = p->n_components ? p->comp_ptr[p->n_components] : 0;
-  for (uint32_t i = 0; i < tot; ++i)
-    if (p->comp_nodes[i] >= p->n_nodes) return fail(LFR_EINVAL, "comp_nodes out of range");
-  return LFR_OK;
-}
-
-template <typename T>
-int upload(T** d, const T* h, size_t count, cudaStream_t s) {
-  *d = nullptr;
-  if (count == 0) return LFR_OK;
-  LFR_CUDA(cudaMalloc((void**)d, count * sizeof(T)));
-  LFR_CUDA(cudaMemcpyAsync(*d, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  // per-edge checks (dst range, self edges) run on the device while the edges are
+  // staged (solve_warp_kernel), so the host never walks the 80-byte records.
   return LFR_OK;
 }
 
@@ -114,44 +129,37 @@ struct lfr_plan {
   uint32_t N = 0, C = 0;
   uint64_t E = 0;
   uint32_t total_slots = 0;
-  uint32_t* d_row_ptr = nullptr;
-  lfr_edge* d_edges = nullptr;
-  uint32_t* d_track = nullptr;
-  uint32_t* d_comp = nullptr;
-  uint8_t* d_is_root = nullptr;
-  uint32_t* d_comp_ptr = nullptr;
-  uint32_t* d_comp_nodes = nullptr;
-  uint32_t* d_local_of = nullptr;
-  double* d_pos = nullptr;
-  double* d_pos_init = nullptr;
-  int32_t* d_iter = nullptr;
-  int32_t* d_term = nullptr;
-  double* d_cost0 = nullptr;
-  double* d_cost1 = nullptr;
-  uint32_t* d_ls = nullptr;
-  uint32_t* d_kept = nullptr;
+  DevBuf row_ptr, edges, track, comp, is_root, comp_ptr, comp_nodes, local_of, pos, pos_init, iter, term, cost0,
+      cost1, ls, kept, cycles, lists, err;
   std::vector<Bucket> buckets;
   std::vector<uint32_t> comp_size;  // nodes per dispatch slot
+  std::vector<uint32_t> list_host;
   uint32_t n_solved = 0;
-  bool solved_once = false;
+  bool profile = false;
+  cudaStream_t streams[kMaxStreams] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxStreams] = {};
+  int n_streams = 0;
 
   lfr::DevProblem dev() const {
     lfr::DevProblem P;
-    P.row_ptr = d_row_ptr;
-    P.edges = reinterpret_cast<const float4*>(d_edges);
-    P.track = d_track;
-    P.comp = d_comp;
-    P.is_root = d_is_root;
-    P.comp_ptr = d_comp_ptr;
-    P.comp_nodes = d_comp_nodes;
-    P.local_of = d_local_of;
-    P.positions = d_pos;
-    P.st_iter = d_iter;
-    P.st_term = d_term;
-    P.st_cost0 = d_cost0;
-    P.st_cost1 = d_cost1;
-    P.st_ls = d_ls;
-    P.st_kept = d_kept;
+    P.n_nodes = N;
+    P.row_ptr = row_ptr.as<uint32_t>();
+    P.edges = edges.as<float4>();
+    P.track = track.as<uint32_t>();
+    P.comp = comp.as<uint32_t>();
+    P.is_root = is_root.as<uint8_t>();
+    P.comp_ptr = comp_ptr.as<uint32_t>();
+    P.comp_nodes = comp_nodes.as<uint32_t>();
+    P.local_of = local_of.as<uint32_t>();
+    P.positions = pos.as<double>();
+    P.st_iter = iter.as<int32_t>();
+    P.st_term = term.as<int32_t>();
+    P.st_cost0 = cost0.as<double>();
+    P.st_cost1 = cost1.as<double>();
+    P.st_ls = ls.as<uint32_t>();
+    P.st_kept = kept.as<uint32_t>();
+    P.st_cycles = profile ? cycles.as<unsigned long long>() : nullptr;
+    P.err_flag = err.as<int>();
     return P;
   }
 };
@@ -160,38 +168,41 @@ namespace {
 
 void free_plan(lfr_plan* pl) {
   if (!pl) return;
-  cudaFree(pl->d_row_ptr);
-  cudaFree(pl->d_edges);
-  cudaFree(pl->d_track);
-  cudaFree(pl->d_comp);
-  cudaFree(pl->d_is_root);
-  cudaFree(pl->d_comp_ptr);
-  cudaFree(pl->d_comp_nodes);
-  cudaFree(pl->d_local_of);
-  cudaFree(pl->d_pos);
-  cudaFree(pl->d_pos_init);
-  cudaFree(pl->d_iter);
-  cudaFree(pl->d_term);
-  cudaFree(pl->d_cost0);
-  cudaFree(pl->d_cost1);
-  cudaFree(pl->d_ls);
-  cudaFree(pl->d_kept);
-  for (Bucket& b : pl->buckets) cudaFree(b.d_list);
+  DevBuf* bufs[] = {&pl->row_ptr, &pl->edges, &pl->track, &pl->comp, &pl->is_root, &pl->comp_ptr, &pl->comp_nodes,
+                    &pl->local_of, &pl->pos, &pl->pos_init, &pl->iter, &pl->term, &pl->cost0, &pl->cost1, &pl->ls,
+                    &pl->kept, &pl->cycles, &pl->lists, &pl->err};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < pl->n_streams; ++i) {
+    if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
+    if (pl->ev_join[i]) cudaEventDestroy(pl->ev_join[i]);
+  }
+  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
   delete pl;
+}
+
+template <typename T>
+int upload(DevBuf* d, const T* h, size_t count, cudaStream_t s) {
+  LFR_TRY(d->reserve(std::max<size_t>(count, 1) * sizeof(T)));
+  if (count) LFR_CUDA(cudaMemcpyAsync(d->p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  return LFR_OK;
 }
 
 // Size-bucketed schedule: components are grouped by the shared memory one warp
 // needs for them, so small tracks run at high occupancy and the few large
-// components do not dictate the carve-up of everyone else.
-int build_buckets(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
+// components do not dictate the carve-up of everyone else.  Buckets are
+// launched on concurrent streams, largest components first.
+int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   static const int kClass[] = {2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 57344, kMaxSmemPerBlock};
   const int n_class = sizeof(kClass) / sizeof(kClass[0]);
   std::vector<std::vector<uint32_t>> members(n_class);
   std::vector<Bucket> caps(n_class);
   pl->comp_size.resize(p->n_components);
   pl->n_solved = 0;
+  pl->buckets.clear();
+  pl->list_host.clear();
   for (uint32_t c = 0; c < p->n_components; ++c) {
     const uint32_t beg = p->comp_ptr[c], end = p->comp_ptr[c + 1];
+    if (end < beg || end > pl->total_slots) return fail(LFR_EINVAL, "comp_ptr not monotone");
     const uint32_t nc = end - beg;
     pl->comp_size[c] = nc;
     if (nc <= 1) continue;  // solve.cc:619-622
@@ -200,15 +211,16 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
     uint32_t nfree = 0;
     for (uint32_t i = beg; i < end; ++i) {
       const uint32_t v = p->comp_nodes[i];
+      if (v >= p->n_nodes) return fail(LFR_EINVAL, "comp_nodes out of range");
+      if (p->row_ptr[v + 1] < p->row_ptr[v]) return fail(LFR_EINVAL, "row_ptr not monotone");
       eup += p->row_ptr[v + 1] - p->row_ptr[v];
       nfree += p->is_root[v] ? 0 : 1;
     }
     const int n2 = 2 * (int)nfree;
     if (n2 > lfr::kMaxWarpN2 || nc > (uint32_t)lfr::kMaxWarpNodes || eup > 65535) {
       char buf[160];
-      snprintf(buf, sizeof buf,
-               "component %u (nodes=%u, unknowns=%d, out-edges=%llu) exceeds the warp-tier caps", c, nc, n2,
-               (unsigned long long)eup);
+      snprintf(buf, sizeof buf, "component %u (nodes=%u, unknowns=%d, out-edges=%llu) exceeds the warp-tier caps",
+               c, nc, n2, (unsigned long long)eup);
       return fail(LFR_EUNSUPPORTED, buf);
     }
     const int e = std::max<int>(1, (int)eup);
@@ -221,28 +233,113 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
     caps[k].ncmax = std::max(caps[k].ncmax, (int)nc);
     caps[k].n2max = std::max(caps[k].n2max, std::max(n2, 2));
   }
-  for (int k = 0; k < n_class; ++k) {
+  for (int k = n_class - 1; k >= 0; --k) {  // largest first
     if (members[k].empty()) continue;
     Bucket b = caps[k];
     b.n = (uint32_t)members[k].size();
+    b.offset = (uint32_t)pl->list_host.size();
     const lfr::WarpLayout L(b.emax, b.ncmax, b.n2max);
     b.smem_per_warp = L.total;
     if (b.smem_per_warp > kMaxSmemPerBlock) return fail(LFR_EUNSUPPORTED, "bucket exceeds shared memory");
     b.warps = (4 * b.smem_per_warp <= kMaxSmemPerBlock) ? 4 : 1;
-    int rc = upload(&b.d_list, members[k].data(), members[k].size(), s);
-    if (rc) return rc;
+    pl->list_host.insert(pl->list_host.end(), members[k].begin(), members[k].end());
     pl->buckets.push_back(b);
   }
   return LFR_OK;
 }
 
+// (Re)fill a plan from host arrays: H2D copies + schedule.  Buffers only grow.
+int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const double* initial_positions,
+              cudaStream_t s) {
+  pl->opt = o;
+  pl->K = make_consts(o);
+  pl->N = p->n_nodes;
+  pl->C = p->n_components;
+  pl->E = p->n_edges;
+  pl->total_slots = p->n_components ? p->comp_ptr[p->n_components] : 0;
+  pl->profile = getenv("LFR_PROFILE") != nullptr;
+  LFR_TRY(upload(&pl->edges, p->edges, (size_t)p->n_edges, s));  // the bulk first
+  LFR_TRY(upload(&pl->row_ptr, p->row_ptr, (size_t)p->n_nodes + 1, s));
+  LFR_TRY(upload(&pl->track, p->track, (size_t)p->n_nodes, s));
+  LFR_TRY(upload(&pl->comp, p->comp, (size_t)p->n_nodes, s));
+  LFR_TRY(upload(&pl->is_root, p->is_root, (size_t)p->n_nodes, s));
+  LFR_TRY(upload(&pl->comp_ptr, p->comp_ptr, (size_t)p->n_components + 1, s));
+  LFR_TRY(upload(&pl->comp_nodes, p->comp_nodes, (size_t)pl->total_slots, s));
+  const size_t N = std::max<size_t>(pl->N, 1), C = std::max<size_t>(pl->C, 1);
+  LFR_TRY(pl->local_of.reserve(sizeof(uint32_t) * N));
+  LFR_TRY(pl->pos.reserve(sizeof(double) * 2 * N));
+  LFR_TRY(pl->pos_init.reserve(sizeof(double) * 2 * N));
+  LFR_TRY(pl->iter.reserve(sizeof(int32_t) * C));
+  LFR_TRY(pl->term.reserve(sizeof(int32_t) * C));
+  LFR_TRY(pl->cost0.reserve(sizeof(double) * C));
+  LFR_TRY(pl->cost1.reserve(sizeof(double) * C));
+  LFR_TRY(pl->ls.reserve(sizeof(uint32_t) * C));
+  LFR_TRY(pl->kept.reserve(sizeof(uint32_t) * C));
+  LFR_TRY(pl->err.reserve(sizeof(int)));
+  if (pl->profile) LFR_TRY(pl->cycles.reserve(sizeof(unsigned long long) * 8 * C));
+  // per-slot stats default to "skipped" (size-1 components never run)
+  LFR_CUDA(cudaMemsetAsync(pl->iter.p, 0, sizeof(int32_t) * C, s));
+  LFR_CUDA(cudaMemsetAsync(pl->term.p, 0, sizeof(int32_t) * C, s));
+  LFR_CUDA(cudaMemsetAsync(pl->cost0.p, 0, sizeof(double) * C, s));
+  LFR_CUDA(cudaMemsetAsync(pl->cost1.p, 0, sizeof(double) * C, s));
+  LFR_CUDA(cudaMemsetAsync(pl->ls.p, 0, sizeof(uint32_t) * C, s));
+  LFR_CUDA(cudaMemsetAsync(pl->kept.p, 0, sizeof(uint32_t) * C, s));
+  LFR_CUDA(cudaMemsetAsync(pl->err.p, 0, sizeof(int), s));
+  if (initial_positions && pl->N)
+    LFR_CUDA(cudaMemcpyAsync(pl->pos_init.p, initial_positions, sizeof(double) * 2 * (size_t)pl->N,
+                             cudaMemcpyHostToDevice, s));
+  else
+    LFR_CUDA(cudaMemsetAsync(pl->pos_init.p, 0, sizeof(double) * 2 * N, s));
+  LFR_TRY(build_buckets(pl, p));  // host work overlaps the copies above
+  LFR_TRY(upload(&pl->lists, pl->list_host.data(), pl->list_host.size(), s));
+  if (pl->total_slots) {
+    lfr::local_index_kernel<<<(pl->total_slots + 255) / 256, 256, 0, s>>>(
+        pl->comp_ptr.as<uint32_t>(), pl->comp_nodes.as<uint32_t>(), pl->C, pl->total_slots,
+        pl->local_of.as<uint32_t>());
+    LFR_CUDA(cudaGetLastError());
+  }
+  // streams for concurrent bucket launches
+  const int want = std::min<int>(kMaxStreams, std::max<int>(0, (int)pl->buckets.size() - 1));
+  if (!pl->ev_fork) LFR_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+  while (pl->n_streams < want) {
+    LFR_CUDA(cudaStreamCreateWithFlags(&pl->streams[pl->n_streams], cudaStreamNonBlocking));
+    LFR_CUDA(cudaEventCreateWithFlags(&pl->ev_join[pl->n_streams], cudaEventDisableTiming));
+    ++pl->n_streams;
+  }
+  return LFR_OK;
+}
+
+int set_kernel_attrs() {
+  static thread_local int done_for_device = -1;
+  int dev = 0;
+  LFR_CUDA(cudaGetDevice(&dev));
+  if (done_for_device == dev) return LFR_OK;
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
+  done_for_device = dev;
+  return LFR_OK;
+}
+
 int launch_solve(lfr_plan* pl, cudaStream_t s) {
-  LFR_CUDA(cudaMemcpyAsync(pl->d_pos, pl->d_pos_init, sizeof(double) * 2 * (size_t)pl->N,
-                           cudaMemcpyDeviceToDevice, s));
+  LFR_TRY(set_kernel_attrs());
+  if (pl->N)
+    LFR_CUDA(cudaMemcpyAsync(pl->pos.p, pl->pos_init.p, sizeof(double) * 2 * (size_t)pl->N,
+                             cudaMemcpyDeviceToDevice, s));
   const lfr::DevProblem P = pl->dev();
-  for (const Bucket& b : pl->buckets) {
+  const int nb = (int)pl->buckets.size();
+  if (nb > 1) LFR_CUDA(cudaEventRecord(pl->ev_fork, s));
+  for (int i = 0; i < nb; ++i) {
+    const Bucket& b = pl->buckets[i];
+    // bucket 0 runs on the caller's stream, the others on side streams forked from it
+    cudaStream_t bs = s;
+    if (i > 0) {
+      bs = pl->streams[(i - 1) % pl->n_streams];
+      LFR_CUDA(cudaStreamWaitEvent(bs, pl->ev_fork, 0));
+    }
     lfr::WarpBucket wb;
-    wb.list = b.d_list;
+    wb.list = pl->lists.as<uint32_t>() + b.offset;
     wb.n = b.n;
     wb.emax = b.emax;
     wb.ncmax = b.ncmax;
@@ -250,20 +347,75 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
     wb.smem_per_warp = b.smem_per_warp;
     const size_t smem = (size_t)b.smem_per_warp * b.warps;
     const unsigned grid = (b.n + b.warps - 1) / b.warps;
-    if (b.warps == 4) {
-      LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kMaxSmemPerBlock));
-      lfr::solve_warp_kernel<4><<<grid, 128, smem, s>>>(P, pl->K, wb);
-    } else {
-      LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kMaxSmemPerBlock));
-      lfr::solve_warp_kernel<1><<<grid, 32, smem, s>>>(P, pl->K, wb);
-    }
+    if (b.warps == 4)
+      lfr::solve_warp_kernel<4><<<grid, 128, smem, bs>>>(P, pl->K, wb);
+    else
+      lfr::solve_warp_kernel<1><<<grid, 32, smem, bs>>>(P, pl->K, wb);
     LFR_CUDA(cudaGetLastError());
   }
-  pl->solved_once = true;
+  for (int k = 0; k < std::min(nb - 1, pl->n_streams); ++k) {  // join the side streams
+    LFR_CUDA(cudaEventRecord(pl->ev_join[k], pl->streams[k]));
+    LFR_CUDA(cudaStreamWaitEvent(s, pl->ev_join[k], 0));
+  }
   return LFR_OK;
 }
+
+int download(lfr_plan* pl, cudaStream_t s, double* positions, lfr_stats* st) {
+  if (positions && pl->N)
+    LFR_CUDA(cudaMemcpyAsync(positions, pl->pos.p, sizeof(double) * 2 * (size_t)pl->N, cudaMemcpyDeviceToHost, s));
+  std::vector<int32_t> it;
+  std::vector<uint32_t> ls;
+  int err = 0;
+  LFR_CUDA(cudaMemcpyAsync(&err, pl->err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (st && pl->C) {
+    it.resize(pl->C);
+    ls.resize(pl->C);
+    LFR_CUDA(cudaMemcpyAsync(it.data(), pl->iter.p, sizeof(int32_t) * pl->C, cudaMemcpyDeviceToHost, s));
+    LFR_CUDA(cudaMemcpyAsync(ls.data(), pl->ls.p, sizeof(uint32_t) * pl->C, cudaMemcpyDeviceToHost, s));
+    if (st->termination)
+      LFR_CUDA(cudaMemcpyAsync(st->termination, pl->term.p, sizeof(int32_t) * pl->C, cudaMemcpyDeviceToHost, s));
+    if (st->initial_cost)
+      LFR_CUDA(cudaMemcpyAsync(st->initial_cost, pl->cost0.p, sizeof(double) * pl->C, cudaMemcpyDeviceToHost, s));
+    if (st->final_cost)
+      LFR_CUDA(cudaMemcpyAsync(st->final_cost, pl->cost1.p, sizeof(double) * pl->C, cudaMemcpyDeviceToHost, s));
+  }
+  LFR_CUDA(cudaStreamSynchronize(s));
+  if (err) return fail(LFR_EINVAL, "edge with dst out of range or a self edge (found while staging edges on the device)");
+  if (st) {
+    uint64_t ti = 0, tl = 0;
+    for (uint32_t c = 0; c < pl->C; ++c) {
+      ti += (uint64_t)it[c];
+      tl += ls[c];
+    }
+    if (st->iterations && pl->C) std::memcpy(st->iterations, it.data(), sizeof(int32_t) * pl->C);
+    st->total_iterations = ti;
+    st->total_line_search_steps = tl;
+    st->n_solved = pl->n_solved;
+    st->n_kernel_launches = (uint32_t)pl->buckets.size();
+  }
+  return LFR_OK;
+}
+
+int select_device(const lfr_options& o) {
+  int n_dev = 0;
+  LFR_CUDA(cudaGetDeviceCount(&n_dev));
+  if (n_dev == 0) return fail(LFR_ENODEV, "no CUDA device");
+  if (o.device < 0 || o.device >= n_dev) return fail(LFR_ENODEV, "device ordinal out of range");
+  LFR_CUDA(cudaSetDevice(o.device));
+  return LFR_OK;
+}
+
+// lfr_solve()'s workspace: one cached plan per host thread and device.
+struct Workspace {
+  lfr_plan* plan[16] = {};
+  cudaEvent_t ev[4] = {};
+  bool have_events = false;
+  ~Workspace() {
+    // device memory is reclaimed at process exit; calling into CUDA from a
+    // thread-local destructor during teardown is not safe.
+  }
+};
+thread_local Workspace g_ws;
 
 }  // namespace
 
@@ -305,81 +457,21 @@ int lfr_plan_create(const lfr_problem* p, const lfr_options* opt, const double* 
                     lfr_plan** out) {
   if (!out) return fail(LFR_EINVAL, "out is NULL");
   *out = nullptr;
-  int rc = validate(p);
-  if (rc) return rc;
+  LFR_TRY(validate(p));
   lfr_options o;
   if (opt) o = *opt; else lfr_options_default(&o);
-  int n_dev = 0;
-  LFR_CUDA(cudaGetDeviceCount(&n_dev));
-  if (n_dev == 0) return fail(LFR_ENODEV, "no CUDA device");
-  if (o.device < 0 || o.device >= n_dev) return fail(LFR_ENODEV, "device ordinal out of range");
-  LFR_CUDA(cudaSetDevice(o.device));
+  LFR_TRY(select_device(o));
   lfr_plan* pl = new lfr_plan();
   pl->device = o.device;
-  pl->opt = o;
-  pl->K = make_consts(o);
-  pl->N = p->n_nodes;
-  pl->C = p->n_components;
-  pl->E = p->n_edges;
-  pl->total_slots = p->n_components ? p->comp_ptr[p->n_components] : 0;
-  cudaStream_t s = 0;
-#define LFR_TRY(expr)          \
-  do {                         \
-    const int rc__ = (expr);   \
-    if (rc__) {                \
-      free_plan(pl);           \
-      return rc__;             \
-    }                          \
-  } while (0)
-  LFR_TRY(upload(&pl->d_row_ptr, p->row_ptr, (size_t)p->n_nodes + 1, s));
-  LFR_TRY(upload(&pl->d_edges, p->edges, (size_t)p->n_edges, s));
-  LFR_TRY(upload(&pl->d_track, p->track, (size_t)p->n_nodes, s));
-  LFR_TRY(upload(&pl->d_comp, p->comp, (size_t)p->n_nodes, s));
-  LFR_TRY(upload(&pl->d_is_root, p->is_root, (size_t)p->n_nodes, s));
-  LFR_TRY(upload(&pl->d_comp_ptr, p->comp_ptr, (size_t)p->n_components + 1, s));
-  LFR_TRY(upload(&pl->d_comp_nodes, p->comp_nodes, (size_t)pl->total_slots, s));
-  auto alloc = [&](void** d, size_t bytes) -> int {
-    *d = nullptr;
-    if (bytes == 0) return LFR_OK;
-    LFR_CUDA(cudaMalloc(d, bytes));
-    LFR_CUDA(cudaMemsetAsync(*d, 0, bytes, s));
-    return LFR_OK;
-  };
-  LFR_TRY(alloc((void**)&pl->d_local_of, sizeof(uint32_t) * (size_t)pl->N));
-  LFR_TRY(alloc((void**)&pl->d_pos, sizeof(double) * 2 * (size_t)pl->N));
-  LFR_TRY(alloc((void**)&pl->d_pos_init, sizeof(double) * 2 * (size_t)pl->N));
-  LFR_TRY(alloc((void**)&pl->d_iter, sizeof(int32_t) * (size_t)pl->C));
-  LFR_TRY(alloc((void**)&pl->d_term, sizeof(int32_t) * (size_t)pl->C));
-  LFR_TRY(alloc((void**)&pl->d_cost0, sizeof(double) * (size_t)pl->C));
-  LFR_TRY(alloc((void**)&pl->d_cost1, sizeof(double) * (size_t)pl->C));
-  LFR_TRY(alloc((void**)&pl->d_ls, sizeof(uint32_t) * (size_t)pl->C));
-  LFR_TRY(alloc((void**)&pl->d_kept, sizeof(uint32_t) * (size_t)pl->C));
-  if (initial_positions && pl->N) {
-    cudaError_t e = cudaMemcpyAsync(pl->d_pos_init, initial_positions, sizeof(double) * 2 * (size_t)pl->N,
-                                    cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) {
-      free_plan(pl);
-      return fail(LFR_ECUDA, cudaGetErrorString(e));
-    }
+  int rc = fill_plan(pl, p, o, initial_positions, 0);
+  if (rc == LFR_OK) {
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) rc = fail(cuda_code(e), cudaGetErrorString(e));
   }
-  LFR_TRY(build_buckets(pl, p, s));
-  if (pl->total_slots) {
-    lfr::local_index_kernel<<<(pl->total_slots + 255) / 256, 256, 0, s>>>(
-        pl->d_comp_ptr, pl->d_comp_nodes, pl->C, pl->total_slots, pl->d_local_of);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-      free_plan(pl);
-      return fail(LFR_ECUDA, cudaGetErrorString(e));
-    }
+  if (rc) {
+    free_plan(pl);
+    return rc;
   }
-  {
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) {
-      free_plan(pl);
-      return fail(LFR_ECUDA, cudaGetErrorString(e));
-    }
-  }
-#undef LFR_TRY
   *out = pl;
   return LFR_OK;
 }
@@ -398,37 +490,7 @@ int lfr_plan_num_launches(const lfr_plan* pl) {
 int lfr_plan_download(lfr_plan* pl, void* stream, double* positions, lfr_stats* st) {
   if (!pl) return fail(LFR_EINVAL, "plan is NULL");
   LFR_CUDA(cudaSetDevice(pl->device));
-  cudaStream_t s = (cudaStream_t)stream;
-  if (positions && pl->N)
-    LFR_CUDA(cudaMemcpyAsync(positions, pl->d_pos, sizeof(double) * 2 * (size_t)pl->N, cudaMemcpyDeviceToHost, s));
-  std::vector<int32_t> it;
-  std::vector<uint32_t> ls;
-  if (st && pl->C) {
-    it.resize(pl->C);
-    ls.resize(pl->C);
-    LFR_CUDA(cudaMemcpyAsync(it.data(), pl->d_iter, sizeof(int32_t) * pl->C, cudaMemcpyDeviceToHost, s));
-    LFR_CUDA(cudaMemcpyAsync(ls.data(), pl->d_ls, sizeof(uint32_t) * pl->C, cudaMemcpyDeviceToHost, s));
-    if (st->termination)
-      LFR_CUDA(cudaMemcpyAsync(st->termination, pl->d_term, sizeof(int32_t) * pl->C, cudaMemcpyDeviceToHost, s));
-    if (st->initial_cost)
-      LFR_CUDA(cudaMemcpyAsync(st->initial_cost, pl->d_cost0, sizeof(double) * pl->C, cudaMemcpyDeviceToHost, s));
-    if (st->final_cost)
-      LFR_CUDA(cudaMemcpyAsync(st->final_cost, pl->d_cost1, sizeof(double) * pl->C, cudaMemcpyDeviceToHost, s));
-  }
-  LFR_CUDA(cudaStreamSynchronize(s));
-  if (st) {
-    uint64_t ti = 0, tl = 0;
-    for (uint32_t c = 0; c < pl->C; ++c) {
-      ti += (uint64_t)it[c];
-      tl += ls[c];
-    }
-    if (st->iterations && pl->C) std::memcpy(st->iterations, it.data(), sizeof(int32_t) * pl->C);
-    st->total_iterations = ti;
-    st->total_line_search_steps = tl;
-    st->n_solved = pl->n_solved;
-    st->n_kernel_launches = (uint32_t)pl->buckets.size();
-  }
-  return LFR_OK;
+  return download(pl, (cudaStream_t)stream, positions, st);
 }
 
 int lfr_plan_traffic(lfr_plan* pl, void* stream, uint64_t* algorithmic_bytes, uint64_t* one_pass_bytes) {
@@ -438,8 +500,8 @@ int lfr_plan_traffic(lfr_plan* pl, void* stream, uint64_t* algorithmic_bytes, ui
   std::vector<int32_t> it(pl->C);
   std::vector<uint32_t> kept(pl->C);
   if (pl->C) {
-    LFR_CUDA(cudaMemcpyAsync(it.data(), pl->d_iter, sizeof(int32_t) * pl->C, cudaMemcpyDeviceToHost, s));
-    LFR_CUDA(cudaMemcpyAsync(kept.data(), pl->d_kept, sizeof(uint32_t) * pl->C, cudaMemcpyDeviceToHost, s));
+    LFR_CUDA(cudaMemcpyAsync(it.data(), pl->iter.p, sizeof(int32_t) * pl->C, cudaMemcpyDeviceToHost, s));
+    LFR_CUDA(cudaMemcpyAsync(kept.data(), pl->kept.p, sizeof(uint32_t) * pl->C, cudaMemcpyDeviceToHost, s));
   }
   LFR_CUDA(cudaStreamSynchronize(s));
   uint64_t alg = 0, one = 0;
@@ -454,6 +516,14 @@ int lfr_plan_traffic(lfr_plan* pl, void* stream, uint64_t* algorithmic_bytes, ui
   return LFR_OK;
 }
 
+/* debug (LFR_PROFILE=1): per-slot cycle counters, 8 x uint64 each */
+int lfr_debug_plan_cycles(lfr_plan* pl, unsigned long long* out) {
+  if (!pl || !pl->profile) return fail(LFR_EINVAL, "plan was not created with LFR_PROFILE=1");
+  LFR_CUDA(cudaSetDevice(pl->device));
+  LFR_CUDA(cudaMemcpy(out, pl->cycles.p, sizeof(unsigned long long) * 8 * (size_t)pl->C, cudaMemcpyDeviceToHost));
+  return LFR_OK;
+}
+
 void lfr_plan_destroy(lfr_plan* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
@@ -461,74 +531,73 @@ void lfr_plan_destroy(lfr_plan* pl) {
 }
 
 int lfr_solve(const lfr_problem* p, const lfr_options* opt, double* positions, lfr_stats* st) {
-  if (p && p->n_nodes && !positions) return fail(LFR_EINVAL, "positions is NULL");
-  lfr_plan* pl = nullptr;
-  cudaEvent_t ev[4];
-  int n_dev = 0;
-  LFR_CUDA(cudaGetDeviceCount(&n_dev));
-  if (n_dev == 0) return fail(LFR_ENODEV, "no CUDA device");
-  LFR_CUDA(cudaSetDevice(opt ? opt->device : 0));
-  for (int i = 0; i < 4; ++i) LFR_CUDA(cudaEventCreate(&ev[i]));
-  cudaStream_t s = 0;
-  LFR_CUDA(cudaEventRecord(ev[0], s));
-  int rc = lfr_plan_create(p, opt, positions, &pl);
-  if (rc) return rc;
-  cudaEventRecord(ev[1], s);
-  rc = launch_solve(pl, s);
-  if (rc) {
-    free_plan(pl);
-    return rc;
+  LFR_TRY(validate(p));
+  if (p->n_nodes && !positions) return fail(LFR_EINVAL, "positions is NULL");
+  lfr_options o;
+  if (opt) o = *opt; else lfr_options_default(&o);
+  LFR_TRY(select_device(o));
+  if (o.device >= 16) return fail(LFR_EUNSUPPORTED, "device ordinal >= 16");
+  Workspace& ws = g_ws;
+  if (!ws.have_events) {
+    for (int i = 0; i < 4; ++i) LFR_CUDA(cudaEventCreate(&ws.ev[i]));
+    ws.have_events = true;
   }
-  cudaEventRecord(ev[2], s);
-  rc = lfr_plan_download(pl, s, positions, st);
-  cudaEventRecord(ev[3], s);
-  cudaEventSynchronize(ev[3]);
-  if (st && rc == LFR_OK) {
+  if (!ws.plan[o.device]) {
+    ws.plan[o.device] = new lfr_plan();
+    ws.plan[o.device]->device = o.device;
+  }
+  lfr_plan* pl = ws.plan[o.device];
+  cudaStream_t s = 0;
+  LFR_CUDA(cudaEventRecord(ws.ev[0], s));
+  LFR_TRY(fill_plan(pl, p, o, positions, s));
+  LFR_CUDA(cudaEventRecord(ws.ev[1], s));
+  LFR_TRY(launch_solve(pl, s));
+  LFR_CUDA(cudaEventRecord(ws.ev[2], s));
+  LFR_TRY(download(pl, s, positions, st));
+  LFR_CUDA(cudaEventRecord(ws.ev[3], s));
+  LFR_CUDA(cudaEventSynchronize(ws.ev[3]));
+  if (st) {
     float a = 0, b = 0, c = 0;
-    cudaEventElapsedTime(&a, ev[0], ev[1]);
-    cudaEventElapsedTime(&b, ev[1], ev[2]);
-    cudaEventElapsedTime(&c, ev[2], ev[3]);
+    cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]);
+    cudaEventElapsedTime(&b, ws.ev[1], ws.ev[2]);
+    cudaEventElapsedTime(&c, ws.ev[2], ws.ev[3]);
     st->h2d_ms = a;
     st->kernel_ms = b;
     st->d2h_ms = c;
     st->total_ms = (double)a + b + c;
   }
-  for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
-  free_plan(pl);
-  return rc;
+  return LFR_OK;
 }
 
 int lfr_debug_edge_eval(const lfr_edge* edges, const uint8_t* kind, uint64_t n, const double* xs,
                         const double* xd, const lfr_options* opt, double* r, double* jac, double* rho) {
   lfr_options o;
   if (opt) o = *opt; else lfr_options_default(&o);
-  int n_dev = 0;
-  LFR_CUDA(cudaGetDeviceCount(&n_dev));
-  if (n_dev == 0) return fail(LFR_ENODEV, "no CUDA device");
-  LFR_CUDA(cudaSetDevice(o.device));
+  LFR_TRY(select_device(o));
   if (n == 0) return LFR_OK;
-  lfr_edge* d_e = nullptr;
-  uint8_t* d_k = nullptr;
-  double *d_xs = nullptr, *d_xd = nullptr, *d_r = nullptr, *d_j = nullptr, *d_rho = nullptr;
-  LFR_CUDA(cudaMalloc((void**)&d_e, n * sizeof(lfr_edge)));
-  LFR_CUDA(cudaMalloc((void**)&d_k, n));
-  LFR_CUDA(cudaMalloc((void**)&d_xs, n * 16));
-  LFR_CUDA(cudaMalloc((void**)&d_xd, n * 16));
-  LFR_CUDA(cudaMalloc((void**)&d_r, n * 16));
-  LFR_CUDA(cudaMalloc((void**)&d_j, n * 32));
-  LFR_CUDA(cudaMalloc((void**)&d_rho, n * 24));
-  LFR_CUDA(cudaMemcpy(d_e, edges, n * sizeof(lfr_edge), cudaMemcpyHostToDevice));
-  LFR_CUDA(cudaMemcpy(d_k, kind, n, cudaMemcpyHostToDevice));
-  LFR_CUDA(cudaMemcpy(d_xs, xs, n * 16, cudaMemcpyHostToDevice));
-  LFR_CUDA(cudaMemcpy(d_xd, xd, n * 16, cudaMemcpyHostToDevice));
-  lfr::edge_eval_kernel<<<(unsigned)((n + 127) / 128), 128>>>(reinterpret_cast<const float4*>(d_e), d_k, n, d_xs,
-                                                             d_xd, make_consts(o), d_r, d_j, d_rho);
-  LFR_CUDA(cudaGetLastError());
-  LFR_CUDA(cudaMemcpy(r, d_r, n * 16, cudaMemcpyDeviceToHost));
-  LFR_CUDA(cudaMemcpy(jac, d_j, n * 32, cudaMemcpyDeviceToHost));
-  LFR_CUDA(cudaMemcpy(rho, d_rho, n * 24, cudaMemcpyDeviceToHost));
-  cudaFree(d_e); cudaFree(d_k); cudaFree(d_xs); cudaFree(d_xd); cudaFree(d_r); cudaFree(d_j); cudaFree(d_rho);
-  return LFR_OK;
+  DevBuf d_e, d_k, d_xs, d_xd, d_r, d_j, d_rho;
+  int rc = LFR_OK;
+  auto run = [&]() -> int {
+    LFR_TRY(upload(&d_e, edges, n, 0));
+    LFR_TRY(upload(&d_k, kind, n, 0));
+    LFR_TRY(upload(&d_xs, xs, 2 * n, 0));
+    LFR_TRY(upload(&d_xd, xd, 2 * n, 0));
+    LFR_TRY(d_r.reserve(n * 16));
+    LFR_TRY(d_j.reserve(n * 32));
+    LFR_TRY(d_rho.reserve(n * 24));
+    lfr::edge_eval_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d_e.as<float4>(), d_k.as<uint8_t>(), n,
+                                                               d_xs.as<double>(), d_xd.as<double>(),
+                                                               make_consts(o), d_r.as<double>(), d_j.as<double>(),
+                                                               d_rho.as<double>());
+    LFR_CUDA(cudaGetLastError());
+    LFR_CUDA(cudaMemcpy(r, d_r.p, n * 16, cudaMemcpyDeviceToHost));
+    LFR_CUDA(cudaMemcpy(jac, d_j.p, n * 32, cudaMemcpyDeviceToHost));
+    LFR_CUDA(cudaMemcpy(rho, d_rho.p, n * 24, cudaMemcpyDeviceToHost));
+    return LFR_OK;
+  };
+  rc = run();
+  d_e.release(); d_k.release(); d_xs.release(); d_xd.release(); d_r.release(); d_j.release(); d_rho.release();
+  return rc;
 }
 
 }  // extern "C"

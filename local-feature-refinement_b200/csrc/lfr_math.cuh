@@ -108,7 +108,19 @@ __device__ __forceinline__ EdgeEval eval_edge(const float4 q[5], int kind, doubl
 }
 
 // ---------------------------------------------------------------------------
-// Line-search step selection (rare path; kept out of line).
+// Line-search step selection (Ceres ArmijoLineSearch, polynomial.cc).
+//
+// Ceres fits the polynomial interpolating {value, gradient} at step 0, at the
+// current trial step and (from the second contraction on) at the previous one,
+// and takes the minimiser over [1e-3, 0.6] x current among: interval middle,
+// interval ends, real parts of all roots of p', and the sample abscissae.  The
+// same interpolant is built here in the normalised variable t = x / h
+// (h = largest sample step), where the two constraints at 0 fix the two lowest
+// coefficients and the rest is a 2x2 (cubic) or 4x4 (quintic) solve — the same
+// polynomial as Ceres' 4x4 / 6x6 Vandermonde solve, better conditioned.  The
+// quartic p' is solved by an Aberth-Ehrlich iteration (= eigenvalues of Ceres'
+// companion matrix) with one root per lane.  oracle/lfr_oracle.cc mirrors this
+// operation for operation.
 // ---------------------------------------------------------------------------
 struct LsSample {
   double x, value, gradient;
@@ -121,29 +133,29 @@ __device__ __forceinline__ double poly_eval(const double* p, int n, double x) {
   return v;
 }
 
-// Real parts of the roots of p (n coefficients, highest degree first); returns
-// the count or -1.  Degree <= 2: closed forms of Ceres polynomial.cc; higher:
-// Aberth-Ehrlich iteration (= eigenvalues of the companion matrix).
-__device__ __noinline__ int poly_roots_real(const double* pin, int nin, double* out) {
+// Real parts of the roots of the polynomial c[0..n-1] (highest degree first,
+// n <= 5).  Returns the count or -1 ("unable to find the critical points").
+// Warp-uniform call; for degree 3/4 lane i < degree iterates root i.
+__device__ __noinline__ int poly_roots_real(const double* c, int n, double* out, int lane) {
   int lead = 0;
-  while (lead + 1 < nin && pin[lead] == 0.0) ++lead;
-  const double* p = pin + lead;
-  const int degree = nin - lead - 1;
+  while (lead + 1 < n && c[lead] == 0.0) ++lead;   // RemoveLeadingZeros
+  const double* p = c + lead;
+  const int degree = n - lead - 1;
   if (degree <= 0) return 0;
   if (degree == 1) {
     out[0] = -p[1] / p[0];
     return 1;
   }
-  if (degree == 2) {
-    const double a = p[0], b = p[1], c = p[2];
-    const double D = b * b - 4 * a * c;
+  if (degree == 2) {  // FindQuadraticPolynomialRoots
+    const double a = p[0], b = p[1], cc = p[2];
+    const double D = b * b - 4 * a * cc;
     const double sq = sqrt(fabs(D));
     if (D >= 0) {
       if (b >= 0) {
         out[0] = (-b - sq) / (2.0 * a);
-        out[1] = (2.0 * c) / (-b - sq);
+        out[1] = (2.0 * cc) / (-b - sq);
       } else {
-        out[0] = (2.0 * c) / (-b + sq);
+        out[0] = (2.0 * cc) / (-b + sq);
         out[1] = (-b + sq) / (2.0 * a);
       }
     } else {
@@ -151,173 +163,171 @@ __device__ __noinline__ int poly_roots_real(const double* pin, int nin, double* 
     }
     return 2;
   }
-  if (degree > 5) return -1;
-  double m[6];
+  double m[5];
+  double bound = 0.0;
   for (int i = 0; i <= degree; ++i) {
     m[i] = p[i] / p[0];
     if (!isfinite(m[i])) return -1;
+    if (i) bound = fmax(bound, fabs(m[i]));
   }
-  double bound = 0.0;
-  for (int i = 1; i <= degree; ++i) bound = fmax(bound, fabs(m[i]));
-  bound += 1.0;
-  double zr[5], zi[5];
-  for (int i = 0; i < degree; ++i) {
-    const double ang = 2.0 * 3.14159265358979323846 * i / degree + 0.4;
-    zr[i] = 0.5 * bound * cos(ang);
-    zi[i] = 0.5 * bound * sin(ang);
-  }
-  for (int it = 0; it < 64; ++it) {
-    double change = 0.0;
-    for (int i = 0; i < degree; ++i) {
-      // Horner for p and p' at z_i (complex)
-      double pr = m[0], pi = 0.0, dr = 0.0, di = 0.0;
-      for (int k = 1; k <= degree; ++k) {
-        const double ndr = dr * zr[i] - di * zi[i] + pr;
-        const double ndi = dr * zi[i] + di * zr[i] + pi;
-        dr = ndr;
-        di = ndi;
-        const double npr = pr * zr[i] - pi * zi[i] + m[k];
-        const double npi = pr * zi[i] + pi * zr[i];
-        pr = npr;
-        pi = npi;
-      }
-      if (pr == 0.0 && pi == 0.0) continue;
-      // newton = p / p'
-      double den = dr * dr + di * di;
-      const double nr = (pr * dr + pi * di) / den, ni = (pi * dr - pr * di) / den;
-      double rr = 0.0, ri = 0.0;  // sum 1/(z_i - z_j)
-      for (int j = 0; j < degree; ++j) {
-        if (j == i) continue;
-        const double ar = zr[i] - zr[j], ai = zi[i] - zi[j];
-        const double d2 = ar * ar + ai * ai;
-        rr += ar / d2;
-        ri -= ai / d2;
-      }
-      // w = newton / (1 - newton * repel)
-      const double qr = 1.0 - (nr * rr - ni * ri), qi = -(nr * ri + ni * rr);
-      den = qr * qr + qi * qi;
-      const double wr = (nr * qr + ni * qi) / den, wi = (ni * qr - nr * qi) / den;
-      zr[i] -= wr;
-      zi[i] -= wi;
-      change = fmax(change, sqrt(wr * wr + wi * wi) / fmax(1e-300, sqrt(zr[i] * zr[i] + zi[i] * zi[i])));
+  bound = 0.5 * (bound + 1.0);
+  const double kCos3[3] = {0.9210609940028851, -0.79777667414035813, -0.12328431986252686};
+  const double kSin3[3] = {0.38941834230865052, 0.60295304808712002, -0.99237139039577016};
+  const double kCos4[4] = {0.9210609940028851, -0.38941834230865036, -0.92106099400288521, 0.38941834230865063};
+  const double kSin4[4] = {0.38941834230865052, 0.9210609940028851, -0.3894183423086503, -0.92106099400288499};
+  const int me = lane < degree ? lane : 0;
+  double zr = bound * (degree == 3 ? kCos3[me % 3] : kCos4[me]);
+  double zi = bound * (degree == 3 ? kSin3[me % 3] : kSin4[me]);
+  for (int it = 0; it < 48; ++it) {
+    // Horner for p and p' at this lane's root
+    double pr = m[0], pi = 0.0, dr = 0.0, di = 0.0;
+    for (int k = 1; k <= degree; ++k) {
+      const double ndr = dr * zr - di * zi + pr;
+      const double ndi = dr * zi + di * zr + pi;
+      dr = ndr;
+      di = ndi;
+      const double npr = pr * zr - pi * zi + m[k];
+      const double npi = pr * zi + pi * zr;
+      pr = npr;
+      pi = npi;
     }
-    if (change < 1e-13) break;  // roots to 1e-13 relative: far below what the step choice resolves
+    double rr = 0.0, ri = 0.0;  // sum_j 1/(z - z_j)
+    for (int j = 0; j < degree; ++j) {
+      const double ojr = __shfl_sync(0xffffffffu, zr, j), oji = __shfl_sync(0xffffffffu, zi, j);
+      if (j == me) continue;
+      const double ar = zr - ojr, ai = zi - oji;
+      const double inv = 1.0 / (ar * ar + ai * ai);
+      rr += ar * inv;
+      ri -= ai * inv;
+    }
+    double wr = 0.0, wi = 0.0;
+    if (!(pr == 0.0 && pi == 0.0)) {
+      const double inv = 1.0 / (dr * dr + di * di);
+      const double nr = (pr * dr + pi * di) * inv, ni = (pi * dr - pr * di) * inv;  // Newton step p/p'
+      const double qr = 1.0 - (nr * rr - ni * ri), qi = -(nr * ri + ni * rr);
+      const double inv2 = 1.0 / (qr * qr + qi * qi);
+      wr = (nr * qr + ni * qi) * inv2;
+      wi = (ni * qr - nr * qi) * inv2;
+    }
+    zr -= wr;
+    zi -= wi;
+    double change = (wr * wr + wi * wi) / fmax(1e-300, zr * zr + zi * zi);
+    if (lane >= degree) change = 0.0;
+    for (int o = 4; o > 0; o >>= 1) change = fmax(change, __shfl_xor_sync(0xffffffffu, change, o));
+    change = __shfl_sync(0xffffffffu, change, 0);
+    if (!(change >= 1e-26)) break;   // |dz| < 1e-13 |z| for every root (or NaN)
   }
+  bool bad = false;
   for (int i = 0; i < degree; ++i) {
-    if (!isfinite(zr[i])) return -1;
-    out[i] = zr[i];
+    out[i] = __shfl_sync(0xffffffffu, zr, i);
+    bad = bad || !isfinite(out[i]);
   }
-  return degree;
+  return bad ? -1 : degree;
 }
 
-// MinimizeInterpolatingPolynomial over [x_min, x_max] for up to 3 samples
-// (value + gradient each => polynomial degree <= 5).
-__device__ __noinline__ double ls_minimize_interpolant(const LsSample* s, int ns, double x_min,
-                                                        double x_max) {
-  int nc = 0;
-  for (int i = 0; i < ns; ++i) nc += (s[i].value_valid ? 1 : 0) + (s[i].gradient_valid ? 1 : 0);
-  const int degree = nc - 1;
-  double A[36], b[6], poly[6];
-  int perm[6];
-  for (int i = 0; i < 36; ++i) A[i] = 0.0;
-  int row = 0;
-  for (int i = 0; i < ns; ++i) {
-    if (s[i].value_valid) {
-      for (int j = 0; j <= degree; ++j) A[row * nc + j] = pow(s[i].x, (double)(degree - j));
-      b[row++] = s[i].value;
+// Minimiser over [lo, hi] (in x) of the Hermite interpolant through (0, f0, g0),
+// (x1, f1, g1) [and (x2, f2, g2) if three == true].  Warp-uniform.
+__device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1, double f1, double g1,
+                                                 bool three, double x2, double f2, double g2, double lo,
+                                                 double hi, int lane) {
+  const double h = three ? fmax(x1, x2) : x1;
+  const double g0h = g0 * h;
+  double c[6];
+  int nc;
+  if (!three) {
+    const double u = f1 - f0 - g0h, v = (g1 - g0) * h;
+    c[0] = v - 2.0 * u;
+    c[1] = 3.0 * u - v;
+    c[2] = g0h;
+    c[3] = f0;
+    nc = 4;
+  } else {
+    double A[4][5];
+    const double ts[2] = {x1 / h, x2 / h};
+    const double fs[2] = {f1, f2}, gs[2] = {g1, g2};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const double t = ts[q], t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
+      A[2 * q][0] = t2; A[2 * q][1] = t3; A[2 * q][2] = t4; A[2 * q][3] = t5;
+      A[2 * q][4] = fs[q] - f0 - g0h * t;
+      A[2 * q + 1][0] = 2.0 * t; A[2 * q + 1][1] = 3.0 * t2; A[2 * q + 1][2] = 4.0 * t3; A[2 * q + 1][3] = 5.0 * t4;
+      A[2 * q + 1][4] = (gs[q] - g0) * h;
     }
-    if (s[i].gradient_valid) {
-      for (int j = 0; j < degree; ++j)
-        A[row * nc + j] = (degree - j) * pow(s[i].x, (double)(degree - j - 1));
-      b[row++] = s[i].gradient;
-    }
-  }
-  // full-pivot Gaussian elimination (Eigen fullPivLu().solve)
-  for (int i = 0; i < nc; ++i) perm[i] = i;
-  for (int k = 0; k < nc; ++k) {
-    int pr = k, pc = k;
-    double best = -1.0;
-    for (int i = k; i < nc; ++i)
-      for (int j = k; j < nc; ++j)
-        if (fabs(A[i * nc + j]) > best) {
-          best = fabs(A[i * nc + j]);
-          pr = i;
-          pc = j;
+    // Gaussian elimination with partial pivoting, fully unrolled (registers)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int i = k + 1; i < 4; ++i) {
+        if (fabs(A[i][k]) > fabs(A[k][k])) {
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const double t = A[k][j];
+            A[k][j] = A[i][j];
+            A[i][j] = t;
+          }
         }
-    if (best == 0.0) break;
-    if (pr != k) {
-      for (int j = 0; j < nc; ++j) {
-        const double t = A[k * nc + j];
-        A[k * nc + j] = A[pr * nc + j];
-        A[pr * nc + j] = t;
       }
-      const double t = b[k];
-      b[k] = b[pr];
-      b[pr] = t;
-    }
-    if (pc != k) {
-      for (int i = 0; i < nc; ++i) {
-        const double t = A[i * nc + k];
-        A[i * nc + k] = A[i * nc + pc];
-        A[i * nc + pc] = t;
+#pragma unroll
+      for (int i = k + 1; i < 4; ++i) {
+        const double mlt = A[i][k] / A[k][k];
+#pragma unroll
+        for (int j = k; j < 5; ++j) A[i][j] -= mlt * A[k][j];
       }
-      const int t = perm[k];
-      perm[k] = perm[pc];
-      perm[pc] = t;
     }
-    for (int i = k + 1; i < nc; ++i) {
-      const double mlt = A[i * nc + k] / A[k * nc + k];
-      if (mlt == 0.0) continue;
-      for (int j = k; j < nc; ++j) A[i * nc + j] -= mlt * A[k * nc + j];
-      b[i] -= mlt * b[k];
+    double d[4];
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+      double acc = A[i][4];
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j) acc -= A[i][j] * d[j];
+      d[i] = acc / A[i][i];
     }
+    c[0] = d[3]; c[1] = d[2]; c[2] = d[1]; c[3] = d[0];
+    c[4] = g0h;
+    c[5] = f0;
+    nc = 6;
   }
-  double yv[6];
-  for (int i = nc - 1; i >= 0; --i) {
-    double acc = b[i];
-    for (int j = i + 1; j < nc; ++j) acc -= A[i * nc + j] * yv[j];
-    yv[i] = (A[i * nc + i] != 0.0) ? acc / A[i * nc + i] : 0.0;
+  const double tlo = lo / h, thi = hi / h;
+  // MinimizePolynomial: middle, ends, real parts of the roots of p'
+  double ox = (lo + hi) / 2.0;
+  double ov = poly_eval(c, nc, ox / h);
+  double v = poly_eval(c, nc, tlo);
+  if (v < ov) { ov = v; ox = lo; }
+  v = poly_eval(c, nc, thi);
+  if (v < ov) { ov = v; ox = hi; }
+  double der[5], roots[4];
+  const int degree = nc - 1;
+  for (int i = 0; i < degree; ++i) der[i] = (degree - i) * c[i];
+  const int nr = poly_roots_real(der, degree, roots, lane);
+  for (int i = 0; i < nr; ++i) {
+    if (roots[i] < tlo || roots[i] > thi) continue;
+    v = poly_eval(c, nc, roots[i]);
+    if (v < ov) { ov = v; ox = roots[i] * h; }
   }
-  for (int i = 0; i < nc; ++i) poly[perm[i]] = yv[i];
-
-  // MinimizePolynomial: middle, ends, then real parts of the roots of p'
-  double ox = (x_min + x_max) / 2.0;
-  double ov = poly_eval(poly, nc, ox);
-  double v = poly_eval(poly, nc, x_min);
-  if (v < ov) { ov = v; ox = x_min; }
-  v = poly_eval(poly, nc, x_max);
-  if (v < ov) { ov = v; ox = x_max; }
-  if (nc > 2) {
-    double der[5], roots[5];
-    for (int i = 0; i < degree; ++i) der[i] = (degree - i) * poly[i];
-    const int nr = poly_roots_real(der, degree, roots);
-    for (int i = 0; i < nr; ++i) {
-      if (roots[i] < x_min || roots[i] > x_max) continue;
-      v = poly_eval(poly, nc, roots[i]);
-      if (v < ov) { ov = v; ox = roots[i]; }
-    }
-  }
-  for (int i = 0; i < ns; ++i) {
-    if (s[i].x < x_min || s[i].x > x_max) continue;
-    v = poly_eval(poly, nc, s[i].x);
-    if (v < ov) { ov = v; ox = s[i].x; }
+  // MinimizeInterpolatingPolynomial: the samples themselves, in order
+  const double sx[3] = {0.0, x1, x2};
+  for (int i = 0; i < (three ? 3 : 2); ++i) {
+    if (sx[i] < lo || sx[i] > hi) continue;
+    v = poly_eval(c, nc, sx[i] / h);
+    if (v < ov) { ov = v; ox = sx[i]; }
   }
   return ox;
 }
 
 // One contraction of ArmijoLineSearch::DoSearch: new trial step from
 // {initial, current [, previous]}.
-__device__ __noinline__ double ls_next_step(const LsSample& initial, const LsSample& previous,
-                                            const LsSample& current, const DevConsts& K) {
+__device__ __forceinline__ double ls_next_step(const LsSample& initial, const LsSample& previous,
+                                               const LsSample& current, const DevConsts& K, int lane) {
   const double min_step = K.ls_max_contraction * current.x;
   const double max_step = K.ls_min_contraction * current.x;
-  if (!current.value_valid) return fmin(fmax(current.x * 0.5, min_step), max_step);
-  LsSample s[3];
-  s[0] = initial;
-  s[1] = current;
-  int ns = 2;
-  if (previous.value_valid) s[ns++] = previous;
-  return ls_minimize_interpolant(s, ns, min_step, max_step);
+  // invalid value (or a non-finite gradient, which only overflow can produce):
+  // Ceres' bisection rule
+  if (!current.value_valid || !current.gradient_valid ||
+      (previous.value_valid && !previous.gradient_valid))
+    return fmin(fmax(current.x * 0.5, min_step), max_step);
+  return hermite_minimizer(initial.value, initial.gradient, current.x, current.value, current.gradient,
+                           previous.value_valid, previous.x, previous.value, previous.gradient, min_step,
+                           max_step, lane);
 }
 
 // warp-wide helpers --------------------------------------------------------

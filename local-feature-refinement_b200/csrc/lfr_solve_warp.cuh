@@ -22,6 +22,8 @@
 namespace lfr {
 
 struct DevProblem {
+  uint32_t n_nodes;
+  int* err_flag;  // set when a malformed edge (dst out of range, self edge) is met
   const uint32_t* row_ptr;
   const float4* edges;  // 5 x float4 per edge
   const uint32_t* track;
@@ -38,6 +40,7 @@ struct DevProblem {
   double* st_cost1;
   uint32_t* st_ls;
   uint32_t* st_kept;  // kept directed edges E_c
+  unsigned long long* st_cycles;  // optional [8 per slot]: total, setup, eval, assemble, lm_step, line search (LFR_PROFILE=1)
 };
 
 struct WarpBucket {
@@ -310,7 +313,7 @@ __device__ __forceinline__ void make_candidate(const WarpCtx& C, double alpha, c
 }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
 solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -343,6 +346,10 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   C.lof = (uint16_t*)(base + L.lof);
   C.edges = P.edges;
 
+  const bool prof = (P.st_cycles != nullptr);
+  long long t_begin = prof ? clock64() : 0, t_mark = t_begin;
+  long long cyc_eval = 0, cyc_asm = 0, cyc_lm = 0, cyc_ls = 0, cyc_setup = 0;
+#define LFR_TICK(acc) do { if (prof) { const long long now__ = clock64(); acc += now__ - t_mark; t_mark = now__; } } while (0)
   // ---- component setup (solve.cc:98-143) --------------------------------------
   const uint32_t nbeg = P.comp_ptr[c];
   const int Nc = (int)(P.comp_ptr[c + 1] - nbeg);
@@ -388,11 +395,15 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
       e = rowstart[lo] + (uint32_t)(k - (int)candptr[lo]);
       const uint32_t v = C.node[lo];
       const uint32_t dst = __float_as_uint(__ldg(&P.edges[5 * (size_t)e + 4].w));
-      int kind = LFR_EDGE_SKIP;
-      if (P.track[v] == P.track[dst]) kind = LFR_EDGE_CAUCHY;          // solve.cc:105
-      else if (P.comp[v] == P.comp[dst]) kind = LFR_EDGE_TUKEY;        // solve.cc:114
-      keep = (kind != LFR_EDGE_SKIP) && !(P.is_root[v] && P.is_root[dst]) && (dst != v);
-      mt = (uint32_t)lo | (P.local_of[dst] << 12) | ((uint32_t)kind << 24);
+      if (dst >= P.n_nodes || dst == v) {
+        *P.err_flag = 1;  // malformed input: reported by the host as LFR_EINVAL
+      } else {
+        int kind = LFR_EDGE_SKIP;
+        if (P.track[v] == P.track[dst]) kind = LFR_EDGE_CAUCHY;          // solve.cc:105
+        else if (P.comp[v] == P.comp[dst]) kind = LFR_EDGE_TUKEY;        // solve.cc:114
+        keep = (kind != LFR_EDGE_SKIP) && !(P.is_root[v] && P.is_root[dst]);
+        mt = (uint32_t)lo | (P.local_of[dst] << 12) | ((uint32_t)kind << 24);
+      }
     }
     const unsigned m = __ballot_sync(kFull, keep);
     if (keep) {
@@ -456,9 +467,12 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     return;
   }
 
+  LFR_TICK(cyc_setup);
   // ---- iteration 0 -----------------------------------------------------------------
   double cost = eval_pass(C, C.x, K);
+  LFR_TICK(cyc_eval);
   double gmax = assemble(C, true, K);
+  LFR_TICK(cyc_asm);
   const double cost0 = cost;
   double radius = K.radius0, nu = 2.0;
   int iter = 0, n_invalid = 0, term = LFR_TERM_NO_CONVERGENCE;
@@ -483,7 +497,9 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     ++iter;
     success = false;
     double model_change = 0.0;
+    LFR_TICK(cyc_ls);
     bool valid = lm_step(C, radius, K, &model_change);
+    LFR_TICK(cyc_lm);
     valid = valid && (model_change > 0.0);
     if (!valid) {
       if (++n_invalid >= K.max_invalid) { term = LFR_TERM_FAILURE; break; }
@@ -500,8 +516,10 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     }
     gd = warp_sum(gd);
     dmax = warp_max(dmax);
+    LFR_TICK(cyc_ls);
     make_candidate(C, 1.0, K);
     double cost_c = eval_pass(C, C.xc, K);
+    LFR_TICK(cyc_eval);
     bool c_valid = isfinite(cost_c);
     if (!c_valid || cost_c > cost + K.ls_suff * gd * 1.0) {
       LsSample initial{0.0, cost, gd, true, true};
@@ -517,7 +535,7 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
         ++ls_iter;
         ++ls_steps;
         if (ls_iter >= K.max_ls_iter) break;
-        const double step = ls_next_step(initial, previous, current, K);
+        const double step = ls_next_step(initial, previous, current, K, lane);
         if (step * dmax < K.ls_min_step) break;
         previous = current;
         make_candidate(C, step, K);
@@ -549,7 +567,9 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
       __syncwarp();
       x_norm = free_norm(C.x, nullptr);
       cost = cost_c;
+      LFR_TICK(cyc_ls);
       gmax = assemble(C, false, K);
+      LFR_TICK(cyc_asm);
       success = true;
       const double t = 2.0 * rho - 1.0;
       radius = fmin(K.radius_max, radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
@@ -570,7 +590,16 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     P.st_cost0[c] = cost0;
     P.st_cost1[c] = cost;
     P.st_ls[c] = ls_steps;
+    if (prof) {
+      LFR_TICK(cyc_ls);
+      unsigned long long* o = P.st_cycles + 8 * (size_t)c;
+      o[0] = (unsigned long long)(t_mark - t_begin);
+      o[1] = cyc_setup; o[2] = cyc_eval; o[3] = cyc_asm; o[4] = cyc_lm; o[5] = cyc_ls;
+      unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      o[6] = smid; o[7] = (unsigned long long)t_begin;
+    }
   }
+#undef LFR_TICK
 }
 
 // node -> index inside its component's node list

@@ -130,207 +130,199 @@ void loss_eval(int kind, double sim, double s, const lfr_options& o,
 }
 
 // ---------------------------------------------------------------------------
-// polynomial.cc — interpolating polynomial + bounded minimisation, used by the
-// Armijo line search.  Coefficients are highest degree first.
+// polynomial.cc — the interpolating polynomial of the Armijo line search and
+// its bounded minimisation.
+//
+// Ceres (FindInterpolatingPolynomial + MinimizePolynomial) fits the polynomial
+// through {value, gradient} at step 0, at the current trial step and, from the
+// second contraction on, at the previous one, by a 4x4 / 6x6 Vandermonde solve
+// (Eigen fullPivLu), and takes the minimiser over [x_min, x_max] among: interval
+// middle, both ends, the real parts of all roots of p' (closed forms up to
+// degree 2, eigenvalues of the balanced companion matrix above), and the sample
+// abscissae.  The restatement builds the SAME polynomial in the normalised
+// variable t = x / h (h = largest sample step): the two constraints at 0 fix
+// the two lowest coefficients, the others come from a 2x2 (closed form) or 4x4
+// (partial pivoting) solve; the companion-matrix eigenvalues are computed as
+// the roots of the monic polynomial by an Aberth-Ehrlich iteration.
+// csrc/lfr_math.cuh mirrors this operation for operation.
 // ---------------------------------------------------------------------------
 struct Sample {
   double x = 0, value = 0, gradient = 0;
   bool value_valid = false, gradient_valid = false;
 };
 
-double poly_eval(const std::vector<double>& p, double x) {
+double poly_eval(const double* p, int n, double x) {
   double v = 0.0;
-  for (double c : p) v = v * x + c;
+  for (int i = 0; i < n; ++i) v = v * x + p[i];
   return v;
 }
 
-std::vector<double> poly_derivative(const std::vector<double>& p) {
-  const int degree = (int)p.size() - 1;
-  if (degree == 0) return std::vector<double>(1, 0.0);
-  std::vector<double> d(degree);
-  for (int i = 0; i < degree; ++i) d[i] = (degree - i) * p[i];
-  return d;
-}
-
-// lhs.fullPivLu().solve(rhs) for the tiny (<= 6x6) Vandermonde-type system.
-std::vector<double> solve_full_pivot(std::vector<double> A, std::vector<double> b,
-                                     int n) {
-  std::vector<int> colperm(n);
-  for (int i = 0; i < n; ++i) colperm[i] = i;
-  for (int k = 0; k < n; ++k) {
-    int pr = k, pc = k;
-    double best = -1.0;
-    for (int i = k; i < n; ++i)
-      for (int j = k; j < n; ++j)
-        if (std::fabs(A[i * n + j]) > best) {
-          best = std::fabs(A[i * n + j]);
-          pr = i;
-          pc = j;
-        }
-    if (best == 0.0) break;
-    if (pr != k) {
-      for (int j = 0; j < n; ++j) std::swap(A[k * n + j], A[pr * n + j]);
-      std::swap(b[k], b[pr]);
-    }
-    if (pc != k) {
-      for (int i = 0; i < n; ++i) std::swap(A[i * n + k], A[i * n + pc]);
-      std::swap(colperm[k], colperm[pc]);
-    }
-    for (int i = k + 1; i < n; ++i) {
-      const double m = A[i * n + k] / A[k * n + k];
-      if (m == 0.0) continue;
-      for (int j = k; j < n; ++j) A[i * n + j] -= m * A[k * n + j];
-      b[i] -= m * b[k];
-    }
-  }
-  std::vector<double> y(n, 0.0);
-  for (int i = n - 1; i >= 0; --i) {
-    double s = b[i];
-    for (int j = i + 1; j < n; ++j) s -= A[i * n + j] * y[j];
-    y[i] = (A[i * n + i] != 0.0) ? s / A[i * n + i] : 0.0;
-  }
-  std::vector<double> x(n);
-  for (int i = 0; i < n; ++i) x[colperm[i]] = y[i];
-  return x;
-}
-
-// FindInterpolatingPolynomial (polynomial.cc)
-std::vector<double> find_interpolating_polynomial(const std::vector<Sample>& s) {
-  int nc = 0;
-  for (const Sample& q : s) nc += (q.value_valid ? 1 : 0) + (q.gradient_valid ? 1 : 0);
-  const int degree = nc - 1;
-  std::vector<double> lhs(nc * nc, 0.0), rhs(nc, 0.0);
-  int row = 0;
-  for (const Sample& q : s) {
-    if (q.value_valid) {
-      for (int j = 0; j <= degree; ++j) lhs[row * nc + j] = std::pow(q.x, degree - j);
-      rhs[row++] = q.value;
-    }
-    if (q.gradient_valid) {
-      for (int j = 0; j < degree; ++j)
-        lhs[row * nc + j] = (degree - j) * std::pow(q.x, degree - j - 1);
-      rhs[row++] = q.gradient;
-    }
-  }
-  return solve_full_pivot(lhs, rhs, nc);
-}
-
-// Roots of a polynomial (real parts returned, as Ceres' callers only look at
-// roots_real).  Degree <= 2 follows polynomial.cc's closed forms; degree >= 3
-// is Ceres' "eigenvalues of the balanced companion matrix", restated here as an
-// Aberth-Ehrlich simultaneous iteration on the same monic polynomial (the
-// eigenvalues of the companion matrix ARE the polynomial's roots).
-bool find_polynomial_roots(const std::vector<double>& pin, std::vector<double>* real) {
-  real->clear();
-  if (pin.empty()) return false;
-  size_t lead = 0;
-  while (lead + 1 < pin.size() && pin[lead] == 0.0) ++lead;  // RemoveLeadingZeros
-  std::vector<double> p(pin.begin() + lead, pin.end());
-  const int degree = (int)p.size() - 1;
-  if (degree == 0) return true;
+// Real parts of the roots of c[0..n-1] (highest degree first, n <= 5).
+// Returns the count, or -1 ("Unable to find the critical points").
+int poly_roots_real(const double* c, int n, double* out) {
+  int lead = 0;
+  while (lead + 1 < n && c[lead] == 0.0) ++lead;  // RemoveLeadingZeros
+  const double* p = c + lead;
+  const int degree = n - lead - 1;
+  if (degree <= 0) return 0;
   if (degree == 1) {
-    real->push_back(-p[1] / p[0]);
-    return true;
+    out[0] = -p[1] / p[0];
+    return 1;
   }
   if (degree == 2) {  // FindQuadraticPolynomialRoots
-    const double a = p[0], b = p[1], c = p[2];
-    const double D = b * b - 4 * a * c;
-    const double sqrt_D = std::sqrt(std::fabs(D));
+    const double a = p[0], b = p[1], cc = p[2];
+    const double D = b * b - 4 * a * cc;
+    const double sq = std::sqrt(std::fabs(D));
     if (D >= 0) {
       if (b >= 0) {
-        real->push_back((-b - sqrt_D) / (2.0 * a));
-        real->push_back((2.0 * c) / (-b - sqrt_D));
+        out[0] = (-b - sq) / (2.0 * a);
+        out[1] = (2.0 * cc) / (-b - sq);
       } else {
-        real->push_back((2.0 * c) / (-b + sqrt_D));
-        real->push_back((-b + sqrt_D) / (2.0 * a));
+        out[0] = (2.0 * cc) / (-b + sq);
+        out[1] = (-b + sq) / (2.0 * a);
       }
     } else {
-      real->push_back(-b / (2.0 * a));
-      real->push_back(-b / (2.0 * a));
+      out[0] = out[1] = -b / (2.0 * a);
     }
-    return true;
+    return 2;
   }
-  typedef std::complex<double> cd;
-  std::vector<double> m(p.size());
-  for (size_t i = 0; i < p.size(); ++i) m[i] = p[i] / p[0];
-  for (double c : m)
-    if (!std::isfinite(c)) return false;
-  double bound = 0.0;  // Cauchy bound on |root|
-  for (int i = 1; i <= degree; ++i) bound = std::max(bound, std::fabs(m[i]));
-  bound += 1.0;
-  std::vector<cd> z(degree);
+  double m[5];
+  double bound = 0.0;
+  for (int i = 0; i <= degree; ++i) {
+    m[i] = p[i] / p[0];
+    if (!std::isfinite(m[i])) return -1;
+    if (i) bound = std::max(bound, std::fabs(m[i]));
+  }
+  bound = 0.5 * (bound + 1.0);
+  static const double kCos3[3] = {0.9210609940028851, -0.79777667414035813, -0.12328431986252686};
+  static const double kSin3[3] = {0.38941834230865052, 0.60295304808712002, -0.99237139039577016};
+  static const double kCos4[4] = {0.9210609940028851, -0.38941834230865036, -0.92106099400288521,
+                                  0.38941834230865063};
+  static const double kSin4[4] = {0.38941834230865052, 0.9210609940028851, -0.3894183423086503,
+                                  -0.92106099400288499};
+  double zr[4], zi[4], wr[4], wi[4];
   for (int i = 0; i < degree; ++i) {
-    const double ang = 2.0 * M_PI * i / degree + 0.4;
-    z[i] = 0.5 * bound * cd(std::cos(ang), std::sin(ang));
+    zr[i] = bound * (degree == 3 ? kCos3[i] : kCos4[i]);
+    zi[i] = bound * (degree == 3 ? kSin3[i] : kSin4[i]);
   }
-  for (int it = 0; it < 64; ++it) {
+  for (int it = 0; it < 48; ++it) {
+    for (int i = 0; i < degree; ++i) {  // all roots from the previous iterate (Jacobi sweep)
+      double pr = m[0], pi = 0.0, dr = 0.0, di = 0.0;
+      for (int k = 1; k <= degree; ++k) {
+        const double ndr = dr * zr[i] - di * zi[i] + pr;
+        const double ndi = dr * zi[i] + di * zr[i] + pi;
+        dr = ndr;
+        di = ndi;
+        const double npr = pr * zr[i] - pi * zi[i] + m[k];
+        const double npi = pr * zi[i] + pi * zr[i];
+        pr = npr;
+        pi = npi;
+      }
+      double rr = 0.0, ri = 0.0;
+      for (int j = 0; j < degree; ++j) {
+        if (j == i) continue;
+        const double ar = zr[i] - zr[j], ai = zi[i] - zi[j];
+        const double inv = 1.0 / (ar * ar + ai * ai);
+        rr += ar * inv;
+        ri -= ai * inv;
+      }
+      wr[i] = wi[i] = 0.0;
+      if (!(pr == 0.0 && pi == 0.0)) {
+        const double inv = 1.0 / (dr * dr + di * di);
+        const double nr = (pr * dr + pi * di) * inv, ni = (pi * dr - pr * di) * inv;
+        const double qr = 1.0 - (nr * rr - ni * ri), qi = -(nr * ri + ni * rr);
+        const double inv2 = 1.0 / (qr * qr + qi * qi);
+        wr[i] = (nr * qr + ni * qi) * inv2;
+        wi[i] = (ni * qr - nr * qi) * inv2;
+      }
+    }
     double change = 0.0;
     for (int i = 0; i < degree; ++i) {
-      cd pv = m[0], dv = 0.0;
-      for (int k = 1; k <= degree; ++k) {
-        dv = dv * z[i] + pv;
-        pv = pv * z[i] + m[k];
-      }
-      if (pv == cd(0.0)) continue;
-      const cd newton = pv / dv;
-      cd repel = 0.0;
-      for (int j = 0; j < degree; ++j)
-        if (j != i) repel += 1.0 / (z[i] - z[j]);
-      const cd w = newton / (1.0 - newton * repel);
-      z[i] -= w;
-      change = std::max(change, std::abs(w) / std::max(1e-300, std::abs(z[i])));
+      zr[i] -= wr[i];
+      zi[i] -= wi[i];
+      change = std::max(change, (wr[i] * wr[i] + wi[i] * wi[i]) /
+                                    std::max(1e-300, zr[i] * zr[i] + zi[i] * zi[i]));
     }
-    if (change < 1e-13) break;  // roots to 1e-13 relative
+    if (!(change >= 1e-26)) break;
   }
   for (int i = 0; i < degree; ++i) {
-    if (!std::isfinite(z[i].real())) return false;
-    real->push_back(z[i].real());
+    if (!std::isfinite(zr[i])) return -1;
+    out[i] = zr[i];
   }
-  return true;
+  return degree;
 }
 
-// MinimizePolynomial (polynomial.cc)
-void minimize_polynomial(const std::vector<double>& p, double x_min, double x_max,
-                         double* optimal_x, double* optimal_value) {
-  *optimal_x = (x_min + x_max) / 2.0;
-  *optimal_value = poly_eval(p, *optimal_x);
-  const double vmin = poly_eval(p, x_min);
-  if (vmin < *optimal_value) {
-    *optimal_value = vmin;
-    *optimal_x = x_min;
-  }
-  const double vmax = poly_eval(p, x_max);
-  if (vmax < *optimal_value) {
-    *optimal_value = vmax;
-    *optimal_x = x_max;
-  }
-  if (p.size() <= 2) return;
-  std::vector<double> roots;
-  if (!find_polynomial_roots(poly_derivative(p), &roots)) return;
-  for (double root : roots) {
-    if (root < x_min || root > x_max) continue;
-    const double v = poly_eval(p, root);
-    if (v < *optimal_value) {
-      *optimal_value = v;
-      *optimal_x = root;
+// MinimizeInterpolatingPolynomial for the samples (0, f0, g0), (x1, f1, g1)
+// [, (x2, f2, g2)] over [lo, hi]; returns the minimiser, *value = p(minimiser).
+double hermite_minimizer(double f0, double g0, double x1, double f1, double g1, bool three, double x2,
+                         double f2, double g2, double lo, double hi, double* value) {
+  const double h = three ? std::max(x1, x2) : x1;
+  const double g0h = g0 * h;
+  double c[6];
+  int nc;
+  if (!three) {
+    const double u = f1 - f0 - g0h, v = (g1 - g0) * h;
+    c[0] = v - 2.0 * u;
+    c[1] = 3.0 * u - v;
+    c[2] = g0h;
+    c[3] = f0;
+    nc = 4;
+  } else {
+    double A[4][5];
+    const double ts[2] = {x1 / h, x2 / h};
+    const double fs[2] = {f1, f2}, gs[2] = {g1, g2};
+    for (int q = 0; q < 2; ++q) {
+      const double t = ts[q], t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
+      A[2 * q][0] = t2; A[2 * q][1] = t3; A[2 * q][2] = t4; A[2 * q][3] = t5;
+      A[2 * q][4] = fs[q] - f0 - g0h * t;
+      A[2 * q + 1][0] = 2.0 * t; A[2 * q + 1][1] = 3.0 * t2; A[2 * q + 1][2] = 4.0 * t3;
+      A[2 * q + 1][3] = 5.0 * t4;
+      A[2 * q + 1][4] = (gs[q] - g0) * h;
     }
-  }
-}
-
-// MinimizeInterpolatingPolynomial (polynomial.cc)
-void minimize_interpolating_polynomial(const std::vector<Sample>& s, double x_min,
-                                       double x_max, double* optimal_x,
-                                       double* optimal_value) {
-  const std::vector<double> p = find_interpolating_polynomial(s);
-  minimize_polynomial(p, x_min, x_max, optimal_x, optimal_value);
-  for (const Sample& q : s) {
-    if (q.x < x_min || q.x > x_max) continue;
-    const double v = poly_eval(p, q.x);
-    if (v < *optimal_value) {
-      *optimal_x = q.x;
-      *optimal_value = v;
+    for (int k = 0; k < 4; ++k) {
+      for (int i = k + 1; i < 4; ++i)
+        if (std::fabs(A[i][k]) > std::fabs(A[k][k]))
+          for (int j = 0; j < 5; ++j) std::swap(A[k][j], A[i][j]);
+      for (int i = k + 1; i < 4; ++i) {
+        const double mlt = A[i][k] / A[k][k];
+        for (int j = k; j < 5; ++j) A[i][j] -= mlt * A[k][j];
+      }
     }
+    double d[4];
+    for (int i = 3; i >= 0; --i) {
+      double acc = A[i][4];
+      for (int j = i + 1; j < 4; ++j) acc -= A[i][j] * d[j];
+      d[i] = acc / A[i][i];
+    }
+    c[0] = d[3]; c[1] = d[2]; c[2] = d[1]; c[3] = d[0];
+    c[4] = g0h;
+    c[5] = f0;
+    nc = 6;
   }
+  const double tlo = lo / h, thi = hi / h;
+  double ox = (lo + hi) / 2.0;  // MinimizePolynomial starts from the middle
+  double ov = poly_eval(c, nc, ox / h);
+  double v = poly_eval(c, nc, tlo);
+  if (v < ov) { ov = v; ox = lo; }
+  v = poly_eval(c, nc, thi);
+  if (v < ov) { ov = v; ox = hi; }
+  double der[5], roots[4];
+  const int degree = nc - 1;
+  for (int i = 0; i < degree; ++i) der[i] = (degree - i) * c[i];
+  const int nr = poly_roots_real(der, degree, roots);
+  for (int i = 0; i < nr; ++i) {
+    if (roots[i] < tlo || roots[i] > thi) continue;
+    v = poly_eval(c, nc, roots[i]);
+    if (v < ov) { ov = v; ox = roots[i] * h; }
+  }
+  const double sx[3] = {0.0, x1, x2};
+  for (int i = 0; i < (three ? 3 : 2); ++i) {
+    if (sx[i] < lo || sx[i] > hi) continue;
+    v = poly_eval(c, nc, sx[i] / h);
+    if (v < ov) { ov = v; ox = sx[i]; }
+  }
+  if (value) *value = ov;
+  return ox;
 }
 
 // ---------------------------------------------------------------------------
@@ -536,15 +528,14 @@ void do_line_search(const Component& C, const lfr_options& o,
     const double min_step = o.max_line_search_step_contraction * current.x;
     const double max_step = o.min_line_search_step_contraction * current.x;
     double step_size;
-    if (!current.value_valid) {
+    if (!current.value_valid || !current.gradient_valid ||
+        (previous.value_valid && !previous.gradient_valid)) {
+      // invalid sample (a non-finite gradient with a finite value needs overflow): bisection rule
       step_size = std::min(std::max(current.x * 0.5, min_step), max_step);
     } else {
-      std::vector<Sample> samples;
-      samples.push_back(initial);
-      samples.push_back(current);
-      if (previous.value_valid) samples.push_back(previous);
-      double unused;
-      minimize_interpolating_polynomial(samples, min_step, max_step, &step_size, &unused);
+      step_size = hermite_minimizer(initial.value, initial.gradient, current.x, current.value,
+                                    current.gradient, previous.value_valid, previous.x, previous.value,
+                                    previous.gradient, min_step, max_step, nullptr);
     }
     if (step_size * dir_max < o.min_line_search_step_size) return;  // failed
     previous = current;
@@ -1032,27 +1023,20 @@ void lfr_ref_loss(int kind, double sim, double s, const lfr_options* opt, double
   loss_eval(kind, sim, s, o, rho);
 }
 
-// samples: [n][5] = {x, value, gradient, value_valid, gradient_valid}
+// samples: [n][5] = {x, value, gradient, value_valid, gradient_valid}; samples[0] is
+// the line search's initial point (x = 0), n = 2 or 3, all entries valid.
 void lfr_ref_minimize_interpolating_polynomial(const double* samples, int n, double x_min,
                                                double x_max, double* optimal_x,
                                                double* optimal_value) {
-  std::vector<Sample> s(n);
-  for (int i = 0; i < n; ++i) {
-    s[i].x = samples[5 * i];
-    s[i].value = samples[5 * i + 1];
-    s[i].gradient = samples[5 * i + 2];
-    s[i].value_valid = samples[5 * i + 3] != 0.0;
-    s[i].gradient_valid = samples[5 * i + 4] != 0.0;
-  }
-  minimize_interpolating_polynomial(s, x_min, x_max, optimal_x, optimal_value);
+  const bool three = n >= 3;
+  *optimal_x = hermite_minimizer(samples[1], samples[2], samples[5], samples[6], samples[7], three,
+                                 three ? samples[10] : 0.0, three ? samples[11] : 0.0,
+                                 three ? samples[12] : 0.0, x_min, x_max, optimal_value);
 }
 
-// roots (real parts) of a polynomial given highest-degree-first; returns count
+// roots (real parts) of a polynomial given highest-degree-first (n <= 5 coefficients)
 int lfr_ref_polynomial_roots(const double* coeffs, int n, double* real_out) {
-  std::vector<double> p(coeffs, coeffs + n), r;
-  if (!find_polynomial_roots(p, &r)) return -1;
-  for (size_t i = 0; i < r.size(); ++i) real_out[i] = r[i];
-  return (int)r.size();
+  return poly_roots_real(coeffs, n, real_out);
 }
 
 }  // extern "C"
