@@ -1,0 +1,80 @@
+"""The C-ABI library loads on a machine without a GPU, exports every symbol the
+headers declare, and refuses to compute without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lfr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(b200):
+    names = declared("lfr.h") + declared("lfr_wire.h")
+    assert "lfr_solve" in names and "lfr_wire_decode_matches" in names and len(names) >= 16
+    for n in names:
+        assert hasattr(b200.lib, n), n
+    assert b200.backend == "b200"
+    from lfr_b200.capi import ABI_SYMBOLS
+    from lfr_b200.wire import WIRE_SYMBOLS
+    assert sorted(ABI_SYMBOLS + WIRE_SYMBOLS) == names
+
+
+def test_oracle_exports_the_same_abi(oracle):
+    for n in declared("lfr.h"):
+        assert hasattr(oracle.lib, n), n
+    assert oracle.backend == "cpu-oracle"
+
+
+def test_struct_layouts_match_the_header(b200, oracle):
+    from lfr_b200.capi import LfrOptions, LfrProblem, LfrStats
+    from lfr_b200 import EDGE_DTYPE
+    assert C.sizeof(LfrProblem) == 72 and C.sizeof(LfrStats) == 88 and EDGE_DTYPE.itemsize == 80
+    for lib in (b200, oracle):     # same defaults from both implementations
+        o = lib.default_options()
+        assert (o.bound, o.cauchy_a, o.tukey_a, o.max_num_iterations) == (1.0, 0.25, 0.0625, 100)
+        assert (o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance) == (1e-4, 1e-8, 1e-4)
+        assert o.min_line_search_step_size == 1e-9 and o.n_threads == 8 and o.linear_solver == 0
+    assert C.sizeof(LfrOptions) == 160
+
+
+def test_ctypes_structs_agree_with_the_c_compiler(tmp_path):
+    import subprocess
+    from lfr_b200.capi import LfrOptions, LfrProblem, LfrStats
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lfr.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(lfr_edge), sizeof(lfr_problem), sizeof(lfr_options), sizeof(lfr_stats), '
+                   'offsetof(lfr_options, n_threads), offsetof(lfr_stats, total_iterations));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [80, C.sizeof(LfrProblem), C.sizeof(LfrOptions), C.sizeof(LfrStats),
+                   LfrOptions.n_threads.offset, LfrStats.total_iterations.offset]
+
+
+def test_no_cpu_fallback_without_a_device(b200):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from lfr_b200 import build_problem, synth
+    p = build_problem(synth.generate("cfg1", scale=0.2))
+    with pytest.raises(RuntimeError, match=r"\(-2\)|no CUDA|CUDA"):
+        b200.solve(p)
+
+
+def test_invalid_problems_are_rejected(oracle):
+    from lfr_b200 import build_problem, synth
+    from lfr_b200.capi import LfrStats
+    p = build_problem(synth.generate("cfg1", scale=0.2))
+    s, keep = oracle.marshal(p)
+    s.n_edges += 1
+    pos = np.zeros((p.graph.n_nodes, 2))
+    assert oracle.lib.lfr_solve(C.byref(s), None, pos.ctypes.data, None) == -1
+    assert b"row_ptr" in oracle.lib.lfr_last_error()
