@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "lfr_solve_warp.cuh"
+#include "lfr_solve_warp2.cuh"
 
 namespace {
 
@@ -105,6 +105,7 @@ struct Bucket {
   uint32_t offset = 0;  // into the bucket-list buffer
   uint32_t n = 0;
   int emax = 0, ncmax = 0, n2max = 0, smem_per_warp = 0, warps = 4;
+  int variant = 0;  // 0: shared-memory Cholesky kernel (n <= 64); 16 / 32: register Gauss-Jordan kernel (n <= variant)
 };
 
 int validate(const lfr_problem* p) {
@@ -194,12 +195,14 @@ int upload(DevBuf* d, const T* h, size_t count, cudaStream_t s) {
 int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   static const int kClass[] = {2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 57344, kMaxSmemPerBlock};
   const int n_class = sizeof(kClass) / sizeof(kClass[0]);
-  std::vector<std::vector<uint32_t>> members(n_class);
-  std::vector<Bucket> caps(n_class);
+  static const int kVariant[3] = {16, 32, 0};
+  std::vector<std::vector<uint32_t>> members(3 * n_class);
+  std::vector<Bucket> caps(3 * n_class);
   pl->comp_size.resize(p->n_components);
   pl->n_solved = 0;
   pl->buckets.clear();
   pl->list_host.clear();
+  const bool force_v1 = getenv("LFR_FORCE_V1") != nullptr;
   for (uint32_t c = 0; c < p->n_components; ++c) {
     const uint32_t beg = p->comp_ptr[c], end = p->comp_ptr[c + 1];
     if (end < beg || end > pl->total_slots) return fail(LFR_EINVAL, "comp_ptr not monotone");
@@ -216,7 +219,7 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       eup += p->row_ptr[v + 1] - p->row_ptr[v];
       nfree += p->is_root[v] ? 0 : 1;
     }
-    const int n2 = 2 * (int)nfree;
+    const int n2 = std::max(2 * (int)nfree, 2);
     if (n2 > lfr::kMaxWarpN2 || nc > (uint32_t)lfr::kMaxWarpNodes || eup > 65535) {
       char buf[160];
       snprintf(buf, sizeof buf, "component %u (nodes=%u, unknowns=%d, out-edges=%llu) exceeds the warp-tier caps",
@@ -224,26 +227,34 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       return fail(LFR_EUNSUPPORTED, buf);
     }
     const int e = std::max<int>(1, (int)eup);
-    const lfr::WarpLayout L(e, (int)nc, std::max(n2, 2));
+    int vi = (n2 <= 16) ? 0 : (n2 <= 32 ? 1 : 2);
+    if (force_v1) vi = 2;
+    const int need = (vi == 2) ? lfr::WarpLayout(e, (int)nc, n2).total : lfr::Warp2Layout(e, (int)nc, n2).total;
     int k = 0;
-    while (k < n_class && L.total > kClass[k]) ++k;
+    while (k < n_class && need > kClass[k]) ++k;
     if (k == n_class) return fail(LFR_EUNSUPPORTED, "component needs more shared memory than one SM has");
-    members[k].push_back(c);
-    caps[k].emax = std::max(caps[k].emax, e);
-    caps[k].ncmax = std::max(caps[k].ncmax, (int)nc);
-    caps[k].n2max = std::max(caps[k].n2max, std::max(n2, 2));
+    Bucket& cb = caps[vi * n_class + k];
+    members[vi * n_class + k].push_back(c);
+    cb.emax = std::max(cb.emax, e);
+    cb.ncmax = std::max(cb.ncmax, (int)nc);
+    cb.n2max = std::max(cb.n2max, n2);
   }
   for (int k = n_class - 1; k >= 0; --k) {  // largest first
-    if (members[k].empty()) continue;
-    Bucket b = caps[k];
-    b.n = (uint32_t)members[k].size();
-    b.offset = (uint32_t)pl->list_host.size();
-    const lfr::WarpLayout L(b.emax, b.ncmax, b.n2max);
-    b.smem_per_warp = L.total;
-    if (b.smem_per_warp > kMaxSmemPerBlock) return fail(LFR_EUNSUPPORTED, "bucket exceeds shared memory");
-    b.warps = (4 * b.smem_per_warp <= kMaxSmemPerBlock) ? 4 : 1;
-    pl->list_host.insert(pl->list_host.end(), members[k].begin(), members[k].end());
-    pl->buckets.push_back(b);
+    for (int vi = 2; vi >= 0; --vi) {
+      const std::vector<uint32_t>& mem = members[vi * n_class + k];
+      if (mem.empty()) continue;
+      Bucket b = caps[vi * n_class + k];
+      b.variant = kVariant[vi];
+      b.n = (uint32_t)mem.size();
+      b.offset = (uint32_t)pl->list_host.size();
+      b.smem_per_warp = (vi == 2) ? lfr::WarpLayout(b.emax, b.ncmax, b.n2max).total
+                                  : lfr::Warp2Layout(b.emax, b.ncmax, b.n2max).total;
+      if (b.smem_per_warp > kMaxSmemPerBlock) return fail(LFR_EUNSUPPORTED, "bucket exceeds shared memory");
+      b.warps = (4 * b.smem_per_warp <= kMaxSmemPerBlock) ? 4 : 1;
+      if (b.warps == 1 && b.variant == 16) b.variant = 32;  // only <1,32> is instantiated for single-warp CTAs
+      pl->list_host.insert(pl->list_host.end(), mem.begin(), mem.end());
+      pl->buckets.push_back(b);
+    }
   }
   return LFR_OK;
 }
@@ -318,6 +329,12 @@ int set_kernel_attrs() {
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp2_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp2_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp2_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
   done_for_device = dev;
   return LFR_OK;
 }
@@ -347,7 +364,13 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
     wb.smem_per_warp = b.smem_per_warp;
     const size_t smem = (size_t)b.smem_per_warp * b.warps;
     const unsigned grid = (b.n + b.warps - 1) / b.warps;
-    if (b.warps == 4)
+    if (b.variant == 16)
+      lfr::solve_warp2_kernel<4, 16><<<grid, 128, smem, bs>>>(P, pl->K, wb);
+    else if (b.variant == 32 && b.warps == 4)
+      lfr::solve_warp2_kernel<4, 32><<<grid, 128, smem, bs>>>(P, pl->K, wb);
+    else if (b.variant == 32)
+      lfr::solve_warp2_kernel<1, 32><<<grid, 32, smem, bs>>>(P, pl->K, wb);
+    else if (b.warps == 4)
       lfr::solve_warp_kernel<4><<<grid, 128, smem, bs>>>(P, pl->K, wb);
     else
       lfr::solve_warp_kernel<1><<<grid, 32, smem, bs>>>(P, pl->K, wb);

@@ -117,10 +117,10 @@ __device__ __forceinline__ EdgeEval eval_edge(const float4 q[5], int kind, doubl
 // same interpolant is built here in the normalised variable t = x / h
 // (h = largest sample step), where the two constraints at 0 fix the two lowest
 // coefficients and the rest is a 2x2 (cubic) or 4x4 (quintic) solve — the same
-// polynomial as Ceres' 4x4 / 6x6 Vandermonde solve, better conditioned.  The
-// quartic p' is solved by an Aberth-Ehrlich iteration (= eigenvalues of Ceres'
-// companion matrix) with one root per lane.  oracle/lfr_oracle.cc mirrors this
-// operation for operation.
+// polynomial as Ceres' 4x4 / 6x6 Vandermonde solve, better conditioned.  Only
+// the real critical points inside the interval can win the minimisation, and
+// those are bracketed exactly (see real_roots_in).  oracle/lfr_oracle.cc
+// mirrors this operation for operation.
 // ---------------------------------------------------------------------------
 struct LsSample {
   double x, value, gradient;
@@ -133,96 +133,133 @@ __device__ __forceinline__ double poly_eval(const double* p, int n, double x) {
   return v;
 }
 
-// Real parts of the roots of the polynomial c[0..n-1] (highest degree first,
-// n <= 5).  Returns the count or -1 ("unable to find the critical points").
-// Warp-uniform call; for degree 3/4 lane i < degree iterates root i.
-__device__ __noinline__ int poly_roots_real(const double* c, int n, double* out, int lane) {
+// ---- real roots of a polynomial inside an interval ---------------------------
+// MinimizePolynomial looks at the real parts of ALL roots of p', but a candidate
+// only wins if its value is strictly below the best of {middle, ends}; on an
+// interval the minimum of p is attained at an end or at a REAL critical point
+// inside it, so complex roots and roots outside [lo, hi] can never be selected.
+// The real roots inside the interval are found exactly and cheaply by
+// recursion on the derivative: between two consecutive critical points a
+// polynomial is monotone, so every sign change brackets exactly one root, which
+// a safeguarded Newton iteration (Numerical Recipes' rtsafe) then polishes.
+__device__ __forceinline__ void horner2(const double* q, int nq, double x, double* f, double* df) {
+  double v = q[0], d = 0.0;
+  for (int i = 1; i < nq; ++i) {
+    d = d * x + v;
+    v = v * x + q[i];
+  }
+  *f = v;
+  *df = d;
+}
+
+__device__ __noinline__ double bracket_root(const double* q, int nq, double a, double b, double fa, double fb) {
+  if (fa == 0.0) return a;
+  if (fb == 0.0) return b;
+  double xl = fa < 0.0 ? a : b, xh = fa < 0.0 ? b : a;
+  double x = 0.5 * (a + b), dxold = fabs(b - a), dx = dxold, f, df;
+  horner2(q, nq, x, &f, &df);
+  for (int it = 0; it < 100; ++it) {
+    if ((((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
+      dxold = dx;
+      dx = 0.5 * (xh - xl);
+      x = xl + dx;
+      if (xl == x) return x;
+    } else {
+      dxold = dx;
+      dx = f / df;
+      const double t = x;
+      x -= dx;
+      if (t == x) return x;
+    }
+    if (fabs(dx) <= 4e-16 * fabs(x)) return x;
+    horner2(q, nq, x, &f, &df);
+    if (f < 0.0) xl = x; else xh = x;
+  }
+  return x;
+}
+
+// Real roots of c[0..n-1] (highest degree first, degree <= 4) inside [lo, hi],
+// ascending.  Degree <= 2 uses the closed forms of Ceres' polynomial.cc.
+__device__ __noinline__ int real_roots_in(const double* c, int n, double lo, double hi, double* out) {
   int lead = 0;
   while (lead + 1 < n && c[lead] == 0.0) ++lead;   // RemoveLeadingZeros
   const double* p = c + lead;
   const int degree = n - lead - 1;
   if (degree <= 0) return 0;
+  int cnt = 0;
   if (degree == 1) {
-    out[0] = -p[1] / p[0];
-    return 1;
+    const double r = -p[1] / p[0];
+    if (r >= lo && r <= hi) out[cnt++] = r;
+    return cnt;
   }
-  if (degree == 2) {  // FindQuadraticPolynomialRoots
+  if (degree == 2) {  // FindQuadraticPolynomialRoots, real case
     const double a = p[0], b = p[1], cc = p[2];
     const double D = b * b - 4 * a * cc;
-    const double sq = sqrt(fabs(D));
-    if (D >= 0) {
-      if (b >= 0) {
-        out[0] = (-b - sq) / (2.0 * a);
-        out[1] = (2.0 * cc) / (-b - sq);
-      } else {
-        out[0] = (2.0 * cc) / (-b + sq);
-        out[1] = (-b + sq) / (2.0 * a);
-      }
+    if (D < 0) return 0;
+    const double sq = sqrt(D);
+    double r0, r1;
+    if (b >= 0) {
+      r0 = (-b - sq) / (2.0 * a);
+      r1 = (2.0 * cc) / (-b - sq);
     } else {
-      out[0] = out[1] = -b / (2.0 * a);
+      r0 = (2.0 * cc) / (-b + sq);
+      r1 = (-b + sq) / (2.0 * a);
     }
-    return 2;
+    if (r1 < r0) { const double t = r0; r0 = r1; r1 = t; }
+    if (r0 >= lo && r0 <= hi) out[cnt++] = r0;
+    if (r1 >= lo && r1 <= hi && r1 != r0) out[cnt++] = r1;
+    return cnt;
   }
-  double m[5];
-  double bound = 0.0;
-  for (int i = 0; i <= degree; ++i) {
-    m[i] = p[i] / p[0];
-    if (!isfinite(m[i])) return -1;
-    if (i) bound = fmax(bound, fabs(m[i]));
-  }
-  bound = 0.5 * (bound + 1.0);
-  const double kCos3[3] = {0.9210609940028851, -0.79777667414035813, -0.12328431986252686};
-  const double kSin3[3] = {0.38941834230865052, 0.60295304808712002, -0.99237139039577016};
-  const double kCos4[4] = {0.9210609940028851, -0.38941834230865036, -0.92106099400288521, 0.38941834230865063};
-  const double kSin4[4] = {0.38941834230865052, 0.9210609940028851, -0.3894183423086503, -0.92106099400288499};
-  const int me = lane < degree ? lane : 0;
-  double zr = bound * (degree == 3 ? kCos3[me % 3] : kCos4[me]);
-  double zi = bound * (degree == 3 ? kSin3[me % 3] : kSin4[me]);
-  for (int it = 0; it < 48; ++it) {
-    // Horner for p and p' at this lane's root
-    double pr = m[0], pi = 0.0, dr = 0.0, di = 0.0;
-    for (int k = 1; k <= degree; ++k) {
-      const double ndr = dr * zr - di * zi + pr;
-      const double ndi = dr * zi + di * zr + pi;
-      dr = ndr;
-      di = ndi;
-      const double npr = pr * zr - pi * zi + m[k];
-      const double npi = pr * zi + pi * zr;
-      pr = npr;
-      pi = npi;
+  // critical points of p inside the interval (roots of p', degree - 1 <= 3)
+  double d[4], crit[3];
+  for (int i = 0; i < degree; ++i) d[i] = (degree - i) * p[i];
+  int ncrit;
+  if (degree == 3) {
+    ncrit = real_roots_in(d, 3, lo, hi, crit);
+  } else {
+    // degree 4: p' is a cubic; its critical points come from the quadratic p''
+    double dd[3], c2[2];
+    for (int i = 0; i < 3; ++i) dd[i] = (3 - i) * d[i];
+    int lead3 = 0;
+    while (lead3 + 1 < 4 && d[lead3] == 0.0) ++lead3;
+    if (lead3 > 0) {
+      ncrit = real_roots_in(d, 4, lo, hi, crit);   // degenerate cubic: closed forms above
+    } else {
+      const int n2 = real_roots_in(dd, 3, lo, hi, c2);
+      ncrit = 0;
+      double a0 = lo, f0, tmp;
+      horner2(d, 4, a0, &f0, &tmp);
+      for (int s = 0; s <= n2; ++s) {
+        const double b0 = (s < n2) ? c2[s] : hi;
+        double f1;
+        horner2(d, 4, b0, &f1, &tmp);
+        if ((f0 <= 0.0 && f1 >= 0.0) || (f0 >= 0.0 && f1 <= 0.0)) {
+          if (!(f0 == 0.0 && f1 == 0.0)) {
+            const double r = bracket_root(d, 4, a0, b0, f0, f1);
+            if (ncrit == 0 || r != crit[ncrit - 1]) crit[ncrit++] = r;
+          }
+        }
+        a0 = b0;
+        f0 = f1;
+      }
     }
-    double rr = 0.0, ri = 0.0;  // sum_j 1/(z - z_j)
-    for (int j = 0; j < degree; ++j) {
-      const double ojr = __shfl_sync(0xffffffffu, zr, j), oji = __shfl_sync(0xffffffffu, zi, j);
-      if (j == me) continue;
-      const double ar = zr - ojr, ai = zi - oji;
-      const double inv = 1.0 / (ar * ar + ai * ai);
-      rr += ar * inv;
-      ri -= ai * inv;
-    }
-    double wr = 0.0, wi = 0.0;
-    if (!(pr == 0.0 && pi == 0.0)) {
-      const double inv = 1.0 / (dr * dr + di * di);
-      const double nr = (pr * dr + pi * di) * inv, ni = (pi * dr - pr * di) * inv;  // Newton step p/p'
-      const double qr = 1.0 - (nr * rr - ni * ri), qi = -(nr * ri + ni * rr);
-      const double inv2 = 1.0 / (qr * qr + qi * qi);
-      wr = (nr * qr + ni * qi) * inv2;
-      wi = (ni * qr - nr * qi) * inv2;
-    }
-    zr -= wr;
-    zi -= wi;
-    double change = (wr * wr + wi * wi) / fmax(1e-300, zr * zr + zi * zi);
-    if (lane >= degree) change = 0.0;
-    for (int o = 4; o > 0; o >>= 1) change = fmax(change, __shfl_xor_sync(0xffffffffu, change, o));
-    change = __shfl_sync(0xffffffffu, change, 0);
-    if (!(change >= 1e-26)) break;   // |dz| < 1e-13 |z| for every root (or NaN)
   }
-  bool bad = false;
-  for (int i = 0; i < degree; ++i) {
-    out[i] = __shfl_sync(0xffffffffu, zr, i);
-    bad = bad || !isfinite(out[i]);
+  double a0 = lo, f0, tmp;
+  horner2(p, degree + 1, a0, &f0, &tmp);
+  for (int s = 0; s <= ncrit; ++s) {
+    const double b0 = (s < ncrit) ? crit[s] : hi;
+    double f1;
+    horner2(p, degree + 1, b0, &f1, &tmp);
+    if ((f0 <= 0.0 && f1 >= 0.0) || (f0 >= 0.0 && f1 <= 0.0)) {
+      if (!(f0 == 0.0 && f1 == 0.0)) {
+        const double r = bracket_root(p, degree + 1, a0, b0, f0, f1);
+        if (cnt == 0 || r != out[cnt - 1]) out[cnt++] = r;
+      }
+    }
+    a0 = b0;
+    f0 = f1;
   }
-  return bad ? -1 : degree;
+  return cnt;
 }
 
 // Minimiser over [lo, hi] (in x) of the Hermite interpolant through (0, f0, g0),
@@ -298,7 +335,7 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
   double der[5], roots[4];
   const int degree = nc - 1;
   for (int i = 0; i < degree; ++i) der[i] = (degree - i) * c[i];
-  const int nr = poly_roots_real(der, degree, roots, lane);
+  const int nr = real_roots_in(der, degree, tlo, thi, roots);
   for (int i = 0; i < nr; ++i) {
     if (roots[i] < tlo || roots[i] > thi) continue;
     v = poly_eval(c, nc, roots[i]);

@@ -13,7 +13,7 @@
 //     from shared memory into the node's 2x2 diagonal block, its gradient pair
 //     and its block row of the packed lower-triangular normal matrix — row
 //     ownership makes the sums atomics-free and bit-reproducible;
-//   * the warp factorises the (<= 64 x 64) damped normal matrix in shared
+//   * the warp factorises the (<= 96 x 96) damped normal matrix in shared
 //     memory (Cholesky with the right-hand side carried as an extra row), and
 //     all trust-region scalars live in registers, identical in every lane.
 #pragma once
@@ -87,7 +87,7 @@ struct WarpLayout {
 };
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kMaxWarpN2 = 64;      // unknowns a warp handles
+constexpr int kMaxWarpN2 = 96;      // unknowns a warp handles
 constexpr int kMaxWarpNodes = 4095; // 12-bit local indices in `meta`
 
 struct WarpCtx {
@@ -240,9 +240,9 @@ __device__ __forceinline__ bool lm_step(const WarpCtx& C, double radius, const D
   bool ok = true;
   for (int j = 0; j < n; ++j) {
     const double* Aj = C.A + tri(j);
-    double s[3];
+    double s[4];
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
+    for (int p = 0; p < 4; ++p) {
       const int i = j + C.lane + 32 * p;
       s[p] = 0.0;
       if (i <= n) {
@@ -259,7 +259,7 @@ __device__ __forceinline__ bool lm_step(const WarpCtx& C, double radius, const D
     }
     const double rs = rsqrt(sjj);
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
+    for (int p = 0; p < 4; ++p) {
       const int i = j + C.lane + 32 * p;
       if (i <= n) C.A[tri(i) + j] = s[p] * rs;
     }
@@ -267,26 +267,29 @@ __device__ __forceinline__ bool lm_step(const WarpCtx& C, double radius, const D
     __syncwarp();
   }
   if (!ok) return false;
-  // back substitution L^T y = z, z = row n of A; lane holds y[lane], y[lane+32]
-  double z0 = (C.lane < n) ? An[C.lane] : 0.0;
-  double z1 = (C.lane + 32 < n) ? An[C.lane + 32] : 0.0;
+  // back substitution L^T y = z, z = row n of A; lane holds y[lane + 32 p]
+  double z[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) z[p] = (C.lane + 32 * p < n) ? An[C.lane + 32 * p] : 0.0;
   for (int i = n - 1; i >= 0; --i) {
     const double* Li = C.A + tri(i);
-    double yi = ((i >> 5) ? z1 : z0) * C.dinv[i];
+    const int slot = i >> 5;
+    double yi = (slot == 0 ? z[0] : (slot == 1 ? z[1] : z[2])) * C.dinv[i];
     yi = __shfl_sync(kFull, yi, i & 31);
-    if (C.lane < i) z0 -= Li[C.lane] * yi;
-    if (C.lane + 32 < i) z1 -= Li[C.lane + 32] * yi;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      if (C.lane + 32 * p < i) z[p] -= Li[C.lane + 32 * p] * yi;
     if (C.lane == (i & 31)) {
-      if (i >> 5) z1 = yi; else z0 = yi;
+      if (slot == 0) z[0] = yi; else if (slot == 1) z[1] = yi; else z[2] = yi;
     }
   }
   double mc = 0.0;
   bool finite = true;
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
+  for (int p = 0; p < 3; ++p) {
     const int i = C.lane + 32 * p;
     if (i < n) {
-      const double y = p ? z1 : z0;
+      const double y = z[p];
       const double hii = C.H[tri(i) + i];
       const double d2 = fmin(fmax(hii, K.min_diag), K.max_diag) / radius;
       const double si = C.S[i];
@@ -596,7 +599,7 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
       o[0] = (unsigned long long)(t_mark - t_begin);
       o[1] = cyc_setup; o[2] = cyc_eval; o[3] = cyc_asm; o[4] = cyc_lm; o[5] = cyc_ls;
       unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      o[6] = smid; o[7] = (unsigned long long)t_begin;
+      o[6] = (unsigned long long)smid | ((unsigned long long)ls_steps << 32); o[7] = (unsigned long long)t_begin;
     }
   }
 #undef LFR_TICK

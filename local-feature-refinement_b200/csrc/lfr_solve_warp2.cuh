@@ -1,0 +1,644 @@
+// lfr_solve_warp2.cuh — latency-optimised warp-per-component solve for
+// components with <= 32 unknowns (all of the exhaustive-pair configs: a
+// component has at most #images nodes, solve.cc:586).
+//
+// A solve of a Fountain-scale graph is a few thousand independent, strictly
+// sequential LM trajectories; its duration is the latency of the slowest one,
+// not bandwidth.  Compared with lfr_solve_warp.cuh (kept for 32 < n <= 64) this
+// kernel shortens every dependent chain of one LM iteration:
+//
+//   * assembly is edge-parallel: each lane combines its directed edge with its
+//     twin (the reverse edge, found once at setup) into the complete 2x2
+//     off-diagonal block of the normal matrix and a 5-value contribution to its
+//     source node's diagonal block / gradient; a node lane then adds its <= deg
+//     contributions.  One owner per written word => no atomics, reproducible.
+//   * the damped normal equations are solved in REGISTERS: lane i holds row i of
+//     (S H S + D^2 | S g) and the warp runs a Gauss-Jordan elimination, the pivot
+//     row broadcast through one shared-memory line (one reciprocal per pivot, no
+//     square roots, no back substitution).  For an SPD matrix the pivots
+//     are the LDL^T pivots, so "pivot <= 0" is exactly the Cholesky failure test.
+//   * warp reductions are batched (several values per butterfly).
+//
+// Inputs whose edges do not come in (src->dst, dst->src) pairs, or that repeat a
+// pair, are still solved (a serial assembly path), just slower.
+#pragma once
+#include "lfr_solve_warp.cuh"
+
+namespace lfr {
+
+struct Warp2Layout {
+  int x, xc, g, S, dl, H, scr, tup, prow;           // doubles (byte offsets)
+  int eidx, meta, node, rowstart, candptr, cnt;     // u32 / i32
+  int twin, outptr, freeof, lof;                    // u16 / i16
+  int ldh, total;
+  __host__ __device__ Warp2Layout(int emax, int ncmax, int n2max) {
+    ldh = n2max | 1;  // odd row stride (in doubles): lanes reading one column hit distinct banks
+    int o = 0;
+    x = o; o += 16 * ncmax;
+    xc = o; o += 16 * ncmax;
+    g = o; o += 8 * n2max;
+    S = o; o += 8 * n2max;
+    dl = o; o += 8 * n2max;
+    H = o; o += 8 * n2max * ldh;
+    scr = o; o += 8 * 7 * emax;
+    tup = o; o += 8 * 5 * emax;
+    prow = o; o += 8 * 2 * 36;  // double-buffered pivot row of the elimination (32 columns, rhs, 1/pivot, pivot)
+    eidx = o; o += 4 * emax;
+    meta = o; o += 4 * emax;
+    node = o; o += 4 * ncmax;
+    rowstart = o; o += 4 * ncmax;
+    candptr = o; o += 4 * (ncmax + 1);
+    cnt = o; o += 4 * 2 * ncmax;
+    twin = o; o += 2 * emax;
+    outptr = o; o += 2 * (ncmax + 1);
+    freeof = o; o += 2 * ncmax;
+    lof = o; o += 2 * (n2max / 2 + 1);
+    total = align_up(o, 16);
+  }
+};
+
+struct Warp2Ctx {
+  int lane, Nc, Ec, nf, n, emax, ldh;
+  bool irregular;
+  double *x, *xc, *g, *S, *dl, *H, *scr, *tup, *prow;
+  int prow_stride;
+  uint32_t *eidx, *meta, *node;
+  uint16_t *twin, *outptr, *lof;
+  int16_t* freeof;
+  const float4* edges;
+};
+
+__device__ __forceinline__ void warp_sum2_max1(double& s0, double& s1, double& m0) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double a = __shfl_xor_sync(kFull, s0, o), b = __shfl_xor_sync(kFull, s1, o),
+                 c = __shfl_xor_sync(kFull, m0, o);
+    s0 += a;
+    s1 += b;
+    m0 = fmax(m0, c);
+  }
+}
+__device__ __forceinline__ void warp_sum2(double& s0, double& s1) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double a = __shfl_xor_sync(kFull, s0, o), b = __shfl_xor_sync(kFull, s1, o);
+    s0 += a;
+    s1 += b;
+  }
+}
+
+// Same staging as eval_pass (lfr_solve_warp.cuh) for the v2 context.
+__device__ __forceinline__ double eval_pass2(const Warp2Ctx& C, const double* xe, const DevConsts& K) {
+  double cost = 0.0;
+  for (int j = C.lane; j < C.Ec; j += 32) {
+    const uint32_t mt = C.meta[j];
+    const int s = mt & 0xfff, d = (mt >> 12) & 0xfff, kind = mt >> 24;
+    const float4* qp = C.edges + 5 * (size_t)C.eidx[j];
+    float4 q[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) q[t] = __ldg(qp + t);
+    const EdgeEval ev = eval_edge(q, kind, xe[2 * s], xe[2 * s + 1], xe[2 * d], xe[2 * d + 1], K);
+    double* sc = C.scr + j;
+    sc[0] = ev.a;
+    sc[C.emax] = ev.r0;
+    sc[2 * C.emax] = ev.r1;
+    sc[3 * C.emax] = ev.m00;
+    sc[4 * C.emax] = ev.m01;
+    sc[5 * C.emax] = ev.m10;
+    sc[6 * C.emax] = ev.m11;
+    cost += ev.half_rho;
+  }
+  cost = warp_sum(cost);
+  __syncwarp();
+  return cost;
+}
+
+// From the staged evaluation: GRAD_ONLY = false -> H (unscaled, full symmetric),
+// g, on the first call the Jacobi scaling S; returns |x - P(x - g)|_inf.
+// GRAD_ONLY = true -> returns grad . dl (phi'(alpha) of the line search).
+template <bool GRAD_ONLY>
+__device__ __forceinline__ double assemble2(const Warp2Ctx& C, bool first, const DevConsts& K) {
+  const int E = C.emax, ldh = C.ldh;
+  if (!GRAD_ONLY) {
+    for (int i = C.lane; i < C.n * ldh; i += 32) C.H[i] = 0.0;
+    __syncwarp();
+  }
+  if (!C.irregular) {
+    for (int e = C.lane; e < C.Ec; e += 32) {
+      const uint32_t mt = C.meta[e];
+      const int fs = C.freeof[mt & 0xfff], fd = C.freeof[(mt >> 12) & 0xfff];
+      const int t = C.twin[e];
+      const double a = C.scr[e], r0 = C.scr[E + e], r1 = C.scr[2 * E + e];
+      const double m00 = C.scr[3 * E + e], m01 = C.scr[4 * E + e], m10 = C.scr[5 * E + e],
+                   m11 = C.scr[6 * E + e];
+      const double at = C.scr[t], rt0 = C.scr[E + t], rt1 = C.scr[2 * E + t];
+      // contribution of e (as out-edge of its source) and of its twin (as in-edge of the same node)
+      C.tup[3 * E + e] = at * rt0 - a * (m00 * r0 + m10 * r1);
+      C.tup[4 * E + e] = at * rt1 - a * (m01 * r0 + m11 * r1);
+      if (!GRAD_ONLY) {
+        C.tup[e] = a * (m00 * m00 + m10 * m10) + at;
+        C.tup[E + e] = a * (m00 * m01 + m10 * m11);
+        C.tup[2 * E + e] = a * (m01 * m01 + m11 * m11) + at;
+        if (fs >= 0 && fd >= 0) {  // block (fs, fd) = -a M^T - a_t M_t
+          const double t00 = C.scr[3 * E + t], t01 = C.scr[4 * E + t], t10 = C.scr[5 * E + t],
+                       t11 = C.scr[6 * E + t];
+          double* h0 = C.H + (2 * fs) * ldh + 2 * fd;
+          h0[0] = -a * m00 - at * t00;
+          h0[1] = -a * m10 - at * t01;
+          h0[ldh] = -a * m01 - at * t10;
+          h0[ldh + 1] = -a * m11 - at * t11;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  double acc = 0.0, gmax = 0.0;
+  if (!C.irregular) {
+    for (int f = C.lane; f < C.nf; f += 32) {
+      const int l = C.lof[f];
+      double d00 = 0., d01 = 0., d11 = 0., g0 = 0., g1 = 0.;
+      for (int j = C.outptr[l]; j < C.outptr[l + 1]; ++j) {
+        g0 += C.tup[3 * E + j];
+        g1 += C.tup[4 * E + j];
+        if (!GRAD_ONLY) {
+          d00 += C.tup[j];
+          d01 += C.tup[E + j];
+          d11 += C.tup[2 * E + j];
+        }
+      }
+      if (GRAD_ONLY) {
+        acc += g0 * C.dl[2 * f] + g1 * C.dl[2 * f + 1];
+      } else {
+        double* hd = C.H + (2 * f) * ldh + 2 * f;
+        hd[0] = d00;
+        hd[1] = d01;
+        hd[ldh] = d01;
+        hd[ldh + 1] = d11;
+        C.g[2 * f] = g0;
+        C.g[2 * f + 1] = g1;
+        if (first) {
+          C.S[2 * f] = 1.0 / (1.0 + sqrt(d00));
+          C.S[2 * f + 1] = 1.0 / (1.0 + sqrt(d11));
+        }
+        const double x0 = C.x[2 * l], x1 = C.x[2 * l + 1];
+        const double p0 = fmin(fmax(x0 - g0, -K.bound), K.bound), p1 = fmin(fmax(x1 - g1, -K.bound), K.bound);
+        gmax = fmax(gmax, fmax(fabs(x0 - p0), fabs(x1 - p1)));
+      }
+    }
+  } else {
+    // serial path for inputs without clean edge twins: one lane accumulates every edge in order
+    if (C.lane == 0) {
+      for (int i = 0; i < C.n; ++i) C.g[i] = 0.0;
+      for (int e = 0; e < C.Ec; ++e) {
+        const uint32_t mt = C.meta[e];
+        const int fs = C.freeof[mt & 0xfff], fd = C.freeof[(mt >> 12) & 0xfff];
+        const double a = C.scr[e], r0 = C.scr[E + e], r1 = C.scr[2 * E + e];
+        const double m00 = C.scr[3 * E + e], m01 = C.scr[4 * E + e], m10 = C.scr[5 * E + e],
+                     m11 = C.scr[6 * E + e];
+        if (fs >= 0) {
+          C.g[2 * fs] -= a * (m00 * r0 + m10 * r1);
+          C.g[2 * fs + 1] -= a * (m01 * r0 + m11 * r1);
+          if (!GRAD_ONLY) {
+            double* hd = C.H + (2 * fs) * ldh + 2 * fs;
+            hd[0] += a * (m00 * m00 + m10 * m10);
+            hd[1] += a * (m00 * m01 + m10 * m11);
+            hd[ldh] += a * (m00 * m01 + m10 * m11);
+            hd[ldh + 1] += a * (m01 * m01 + m11 * m11);
+          }
+        }
+        if (fd >= 0) {
+          C.g[2 * fd] += a * r0;
+          C.g[2 * fd + 1] += a * r1;
+          if (!GRAD_ONLY) {
+            C.H[(2 * fd) * ldh + 2 * fd] += a;
+            C.H[(2 * fd + 1) * ldh + 2 * fd + 1] += a;
+          }
+        }
+        if (!GRAD_ONLY && fs >= 0 && fd >= 0) {
+          double* h0 = C.H + (2 * fs) * ldh + 2 * fd;
+          double* h1 = C.H + (2 * fd) * ldh + 2 * fs;
+          h0[0] -= a * m00; h0[1] -= a * m10; h0[ldh] -= a * m01; h0[ldh + 1] -= a * m11;
+          h1[0] -= a * m00; h1[1] -= a * m01; h1[ldh] -= a * m10; h1[ldh + 1] -= a * m11;
+        }
+      }
+    }
+    __syncwarp();
+    for (int i = C.lane; i < C.n; i += 32) {
+      if (GRAD_ONLY) {
+        acc += C.g[i] * C.dl[i];
+      } else {
+        if (first) C.S[i] = 1.0 / (1.0 + sqrt(C.H[i * ldh + i]));
+        const int l = C.lof[i >> 1];
+        const double xi = C.x[2 * l + (i & 1)];
+        const double p = fmin(fmax(xi - C.g[i], -K.bound), K.bound);
+        gmax = fmax(gmax, fabs(xi - p));
+      }
+    }
+  }
+  __syncwarp();
+  if (GRAD_ONLY) return warp_sum(acc);
+  return warp_max(gmax);
+}
+
+// (S H S + D^2) y = S g by Gauss-Jordan elimination with the rows in registers
+// (lane i <-> row i, n <= NREG <= 32).  Writes dl = -S y; returns validity and
+// {model_cost_change, g . dl, |dl|_inf}.
+template <int NREG>
+__device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const DevConsts& K,
+                                         double* model_change, double* gd, double* dmax) {
+  const int n = C.n, i = C.lane;
+  const bool act = i < n;
+  const double si = act ? C.S[i] : 0.0;
+  const double gi = act ? C.g[i] : 0.0;
+  const double* Hi = C.H + (act ? i : 0) * C.ldh;
+  const double hii = act ? Hi[i] * si * si : 1.0;
+  const double d2 = act ? fmin(fmax(hii, K.min_diag), K.max_diag) / radius : 0.0;
+  double a[NREG];
+#pragma unroll
+  for (int k = 0; k < NREG; ++k) {
+    double v = 0.0;
+    if (k < n && act) v = Hi[k] * si * C.S[k];
+    if (k == i) v = act ? v + d2 : 1.0;  // idle lanes carry identity rows
+    a[k] = v;
+  }
+  const double b0 = si * gi;
+  double b = b0;
+  bool ok = true;
+  // Gauss-Jordan: the pivot lane normalises its row and broadcasts it through a
+  // double-buffered shared-memory line (one broadcast LDS per element instead of
+  // two shuffles); every other lane eliminates the pivot column from its own row.
+  // The register row is shifted left by one column per step, so slot 0 always
+  // holds the current pivot column and ONE compact loop body serves every column
+  // (a fully unrolled elimination is ~100 KB of straight-line code and stalls on
+  // instruction fetch).
+  // Pivot rows are left un-normalised (the pivot lane only has to publish its
+  // registers), every lane scales its own multiplier with the published
+  // reciprocal, and the reciprocal of the NEXT pivot is computed by all lanes
+  // right after the first update of the step, in the shadow of the remaining
+  // ones: the dependent chain of a step is STS -> LDS -> DMUL -> DFMA.
+  double rp = 1.0 / a[0], myrp = 1.0;
+  for (int j = 0; j < n; ++j) {
+    const int m = n - j;  // live columns j .. n-1 sit in slots 0 .. m-1
+    double* buf = C.prow + (j & 1) * C.prow_stride;
+    if (i == j) {
+      myrp = rp;
+      buf[NREG + 1] = rp;
+      buf[NREG + 2] = a[0];
+#pragma unroll
+      for (int k = 1; k < NREG; ++k) {
+        if (k < m) buf[k] = a[k];
+      }
+      buf[NREG] = b;
+    }
+    __syncwarp();
+    const double f = (i == j) ? 0.0 : a[0] * buf[NREG + 1];  // the pivot row itself is kept
+    if (1 < m) a[0] = a[1] - f * buf[1];
+    rp = 1.0 / a[0];  // look-ahead: meaningful in lane j + 1
+#pragma unroll
+    for (int k = 2; k < NREG; ++k) {
+      if (k < m) a[k - 1] = a[k] - f * buf[k];
+    }
+    b -= f * buf[NREG];
+    const double piv = buf[NREG + 2];
+    ok = ok && (piv > 0.0) && isfinite(piv);
+  }
+  const double y = b * myrp;  // row i now reads  piv_i * y_i = b_i
+  double mc = 0.0, dot = 0.0, mx = 0.0;
+  bool finite = true;
+  if (act) {
+    const double d = -si * y;
+    C.dl[i] = d;
+    mc = y * (b0 + d2 * y);
+    dot = gi * d;
+    mx = fabs(d);
+    finite = isfinite(y);
+  }
+  warp_sum2_max1(mc, dot, mx);
+  *model_change = 0.5 * mc;
+  *gd = dot;
+  *dmax = mx;
+  finite = __all_sync(kFull, finite);
+  __syncwarp();
+  return ok && finite;
+}
+
+__device__ __forceinline__ void make_candidate2(const Warp2Ctx& C, double alpha, const DevConsts& K) {
+  for (int i = C.lane; i < 2 * C.Nc; i += 32) {
+    const int f = C.freeof[i >> 1];
+    double v = C.x[i];
+    if (f >= 0) v = fmin(fmax(v + alpha * C.dl[2 * f + (i & 1)], -K.bound), K.bound);
+    C.xc[i] = v;
+  }
+  __syncwarp();
+}
+
+template <int WARPS, int NREG>
+__global__ void __launch_bounds__(WARPS * 32, (NREG > 16 ? 8 : 12) / WARPS)
+solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t item = blockIdx.x * WARPS + wib;
+  if (item >= B.n) return;  // warps are independent: no block-level barrier anywhere
+  const uint32_t c = B.list[item];
+  unsigned char* base = smem_raw + (size_t)wib * B.smem_per_warp;
+  const Warp2Layout L(B.emax, B.ncmax, B.n2max);
+  Warp2Ctx C;
+  C.lane = lane;
+  C.emax = B.emax;
+  C.ldh = L.ldh;
+  C.x = (double*)(base + L.x);
+  C.xc = (double*)(base + L.xc);
+  C.g = (double*)(base + L.g);
+  C.S = (double*)(base + L.S);
+  C.dl = (double*)(base + L.dl);
+  C.H = (double*)(base + L.H);
+  C.scr = (double*)(base + L.scr);
+  C.tup = (double*)(base + L.tup);
+  C.prow = (double*)(base + L.prow);
+  C.prow_stride = 36;
+  C.eidx = (uint32_t*)(base + L.eidx);
+  C.meta = (uint32_t*)(base + L.meta);
+  C.node = (uint32_t*)(base + L.node);
+  uint32_t* rowstart = (uint32_t*)(base + L.rowstart);
+  uint32_t* candptr = (uint32_t*)(base + L.candptr);
+  int* cnt = (int*)(base + L.cnt);
+  C.twin = (uint16_t*)(base + L.twin);
+  C.outptr = (uint16_t*)(base + L.outptr);
+  C.freeof = (int16_t*)(base + L.freeof);
+  C.lof = (uint16_t*)(base + L.lof);
+  C.edges = P.edges;
+
+  const bool prof = (P.st_cycles != nullptr);
+  long long t_begin = prof ? clock64() : 0, t_mark = t_begin;
+  long long cyc_eval = 0, cyc_asm = 0, cyc_lm = 0, cyc_ls = 0, cyc_setup = 0;
+#define LFR_TICK(acc) do { if (prof) { const long long now__ = clock64(); acc += now__ - t_mark; t_mark = now__; } } while (0)
+
+  // ---- component setup (solve.cc:98-143) --------------------------------------
+  const uint32_t nbeg = P.comp_ptr[c];
+  const int Nc = (int)(P.comp_ptr[c + 1] - nbeg);
+  C.Nc = Nc;
+  int run = 0;
+  for (int l0 = 0; l0 < Nc; l0 += 32) {
+    const int l = l0 + lane;
+    int d = 0;
+    if (l < Nc) {
+      const uint32_t v = P.comp_nodes[nbeg + l];
+      const uint32_t rs = P.row_ptr[v];
+      d = (int)(P.row_ptr[v + 1] - rs);
+      C.node[l] = v;
+      rowstart[l] = rs;
+      cnt[l] = 0;
+      cnt[B.ncmax + l] = 0;
+      double p0 = P.positions[2 * (size_t)v], p1 = P.positions[2 * (size_t)v + 1];
+      if (!P.is_root[v]) {  // IterationZero: x <- Plus(x, 0) projects the start point
+        p0 = fmin(fmax(p0, -K.bound), K.bound);
+        p1 = fmin(fmax(p1, -K.bound), K.bound);
+      }
+      C.x[2 * l] = p0;
+      C.x[2 * l + 1] = p1;
+    }
+    const int inc = warp_incl_scan(d, lane);
+    if (l < Nc) candptr[l] = run + inc - d;
+    run += __shfl_sync(kFull, inc, 31);
+  }
+  if (lane == 0) candptr[Nc] = run;
+  __syncwarp();
+  const int Eup = run;
+  int kept = 0;
+  for (int k0 = 0; k0 < Eup; k0 += 32) {
+    const int k = k0 + lane;
+    bool keep = false;
+    uint32_t e = 0, mt = 0;
+    if (k < Eup) {
+      int lo = 0, hi = Nc - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)candptr[mid] <= k) lo = mid; else hi = mid - 1;
+      }
+      e = rowstart[lo] + (uint32_t)(k - (int)candptr[lo]);
+      const uint32_t v = C.node[lo];
+      const uint32_t dst = __float_as_uint(__ldg(&P.edges[5 * (size_t)e + 4].w));
+      if (dst >= P.n_nodes || dst == v) {
+        *P.err_flag = 1;  // malformed input: reported by the host as LFR_EINVAL
+      } else {
+        int kind = LFR_EDGE_SKIP;
+        if (P.track[v] == P.track[dst]) kind = LFR_EDGE_CAUCHY;          // solve.cc:105
+        else if (P.comp[v] == P.comp[dst]) kind = LFR_EDGE_TUKEY;        // solve.cc:114
+        keep = (kind != LFR_EDGE_SKIP) && !(P.is_root[v] && P.is_root[dst]);
+        if (keep) {
+          const uint32_t dl_ = P.local_of[dst];
+          mt = (uint32_t)lo | (dl_ << 12) | ((uint32_t)kind << 24);
+          atomicAdd(&cnt[lo], 1);              // kept out-degree (integer: order-independent)
+          atomicAdd(&cnt[B.ncmax + dl_], 1);   // kept in-degree
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(kFull, keep);
+    if (keep) {
+      const int pos = kept + __popc(m & ((1u << lane) - 1u));
+      C.eidx[pos] = e;
+      C.meta[pos] = mt;
+    }
+    kept += __popc(m);
+  }
+  __syncwarp();
+  const int Ec = kept;
+  C.Ec = Ec;
+  int orun = 0, frun = 0;
+  for (int l0 = 0; l0 < Nc; l0 += 32) {
+    const int l = l0 + lane;
+    const int co = (l < Nc) ? cnt[l] : 0, ci = (l < Nc) ? cnt[B.ncmax + l] : 0;
+    const int so = warp_incl_scan(co, lane);
+    const bool is_free = (l < Nc) && (co + ci > 0) && !P.is_root[C.node[l < Nc ? l : 0]];
+    const int sf = warp_incl_scan(is_free ? 1 : 0, lane);
+    if (l < Nc) {
+      C.outptr[l] = (uint16_t)(orun + so - co);
+      C.freeof[l] = is_free ? (int16_t)(frun + sf - 1) : (int16_t)-1;
+      if (is_free) C.lof[frun + sf - 1] = (uint16_t)l;
+    }
+    orun += __shfl_sync(kFull, so, 31);
+    frun += __shfl_sync(kFull, sf, 31);
+  }
+  if (lane == 0) C.outptr[Nc] = (uint16_t)orun;
+  __syncwarp();
+  // twin of every kept edge: the unique kept edge dst -> src
+  bool irregular = false;
+  for (int e = lane; e < Ec; e += 32) {
+    const uint32_t mt = C.meta[e];
+    const int s = mt & 0xfff, d = (mt >> 12) & 0xfff;
+    int found = 0, tw = e;
+    for (int j = C.outptr[d]; j < C.outptr[d + 1]; ++j)
+      if ((int)((C.meta[j] >> 12) & 0xfff) == s) {
+        tw = j;
+        ++found;
+      }
+    irregular = irregular || (found != 1);
+    C.twin[e] = (uint16_t)tw;
+  }
+  C.irregular = __any_sync(kFull, irregular);
+  const int nf = frun;
+  C.nf = nf;
+  C.n = 2 * nf;
+  __syncwarp();
+  if (lane == 0) P.st_kept[c] = (uint32_t)Ec;
+  if (nf == 0) {  // "No non-constant parameter blocks found."
+    if (lane == 0) {
+      P.st_iter[c] = 0;
+      P.st_term[c] = LFR_TERM_EMPTY;
+      P.st_cost0[c] = 0.0;
+      P.st_cost1[c] = 0.0;
+      P.st_ls[c] = 0;
+    }
+    return;
+  }
+  LFR_TICK(cyc_setup);
+
+  // ---- iteration 0 -----------------------------------------------------------------
+  double cost = eval_pass2(C, C.x, K);
+  LFR_TICK(cyc_eval);
+  double gmax = assemble2<false>(C, true, K);
+  LFR_TICK(cyc_asm);
+  const double cost0 = cost;
+  double radius = K.radius0, nu = 2.0;
+  int iter = 0, n_invalid = 0, term = LFR_TERM_NO_CONVERGENCE;
+  unsigned ls_steps = 0;
+  bool success = true;
+  // |x|^2 and |x - xc|^2 over the free coordinates in one butterfly
+  auto norms = [&](double* xn2, double* dn2) {
+    double a = 0.0, b = 0.0;
+    for (int i = lane; i < C.n; i += 32) {
+      const int l = C.lof[i >> 1];
+      const double xv = C.x[2 * l + (i & 1)], dv = xv - C.xc[2 * l + (i & 1)];
+      a += xv * xv;
+      b += dv * dv;
+    }
+    warp_sum2(a, b);
+    *xn2 = a;
+    *dn2 = b;
+  };
+  double x_norm;
+  {
+    double a = 0.0;
+    for (int i = lane; i < C.n; i += 32) {
+      const int l = C.lof[i >> 1];
+      const double xv = C.x[2 * l + (i & 1)];
+      a += xv * xv;
+    }
+    x_norm = sqrt(warp_sum(a));
+  }
+
+  // ---- trust-region loop (A.6) ---------------------------------------------------------
+  for (;;) {
+    if (iter >= K.max_iter) { term = LFR_TERM_NO_CONVERGENCE; break; }
+    if (success && gmax <= K.g_tol) { term = LFR_TERM_GRADIENT_TOL; break; }
+    if (radius <= K.radius_min) { term = LFR_TERM_MIN_RADIUS; break; }
+    ++iter;
+    success = false;
+    double model_change = 0.0, gd = 0.0, dmax = 0.0;
+    LFR_TICK(cyc_ls);
+    bool valid = lm_step2<NREG>(C, radius, K, &model_change, &gd, &dmax);
+    LFR_TICK(cyc_lm);
+    valid = valid && (model_change > 0.0);
+    if (!valid) {
+      if (++n_invalid >= K.max_invalid) { term = LFR_TERM_FAILURE; break; }
+      radius /= nu;
+      nu *= 2.0;
+      continue;
+    }
+    n_invalid = 0;
+    // projected Armijo line search along dl (bounds-constrained problem, A.7b)
+    make_candidate2(C, 1.0, K);
+    double cost_c = eval_pass2(C, C.xc, K);
+    LFR_TICK(cyc_eval);
+    bool c_valid = isfinite(cost_c);
+    if (!c_valid || cost_c > cost + K.ls_suff * gd * 1.0) {
+      LsSample initial{0.0, cost, gd, true, true};
+      LsSample previous{0.0, 0.0, 0.0, false, false};
+      LsSample current{1.0, cost_c, 0.0, c_valid, false};
+      if (c_valid) {
+        current.gradient = assemble2<true>(C, false, K);
+        current.gradient_valid = isfinite(current.gradient);
+      }
+      int ls_iter = 0;
+      bool ls_ok = false;
+      for (;;) {
+        ++ls_iter;
+        ++ls_steps;
+        if (ls_iter >= K.max_ls_iter) break;
+        const double step = ls_next_step(initial, previous, current, K, lane);
+        if (step * dmax < K.ls_min_step) break;
+        previous = current;
+        make_candidate2(C, step, K);
+        cost_c = eval_pass2(C, C.xc, K);
+        c_valid = isfinite(cost_c);
+        current = LsSample{step, cost_c, 0.0, c_valid, false};
+        if (c_valid) {
+          current.gradient = assemble2<true>(C, false, K);
+          current.gradient_valid = isfinite(current.gradient);
+        }
+        if (c_valid && !(cost_c > cost + K.ls_suff * gd * step)) { ls_ok = true; break; }
+      }
+      if (ls_ok) {
+        for (int i = lane; i < C.n; i += 32) C.dl[i] *= current.x;
+        __syncwarp();
+      } else {  // line search failed: delta unchanged, candidate = P(x + delta)
+        make_candidate2(C, 1.0, K);
+        cost_c = eval_pass2(C, C.xc, K);
+        c_valid = isfinite(cost_c);
+      }
+    }
+    if (!c_valid) cost_c = 1.7976931348623157e308;
+    double xn2, dn2;
+    norms(&xn2, &dn2);
+    const double step_norm = sqrt(dn2);
+    if (step_norm <= K.p_tol * (x_norm + K.p_tol)) { term = LFR_TERM_PARAMETER_TOL; break; }
+    if (fabs(cost - cost_c) <= K.f_tol * cost) { term = LFR_TERM_FUNCTION_TOL; break; }
+    const double rho = (cost - cost_c) / model_change;
+    if (rho > K.min_rel_decrease) {
+      double a2 = 0.0;
+      for (int i = lane; i < 2 * Nc; i += 32) {
+        const double v = C.xc[i];
+        C.x[i] = v;
+        if (C.freeof[i >> 1] >= 0) a2 += v * v;
+      }
+      __syncwarp();
+      cost = cost_c;
+      LFR_TICK(cyc_ls);
+      gmax = assemble2<false>(C, false, K);
+      x_norm = sqrt(warp_sum(a2));
+      LFR_TICK(cyc_asm);
+      success = true;
+      const double t = 2.0 * rho - 1.0;
+      radius = fmin(K.radius_max, radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+      nu = 2.0;
+    } else {
+      radius /= nu;
+      nu *= 2.0;
+    }
+  }
+  // ---- write back the last accepted x ---------------------------------------------------
+  for (int i = lane; i < C.n; i += 32) {
+    const int l = C.lof[i >> 1];
+    P.positions[2 * (size_t)C.node[l] + (i & 1)] = C.x[2 * l + (i & 1)];
+  }
+  if (lane == 0) {
+    P.st_iter[c] = iter;
+    P.st_term[c] = term;
+    P.st_cost0[c] = cost0;
+    P.st_cost1[c] = cost;
+    P.st_ls[c] = ls_steps;
+    if (prof) {
+      LFR_TICK(cyc_ls);
+      unsigned long long* o = P.st_cycles + 8 * (size_t)c;
+      o[0] = (unsigned long long)(t_mark - t_begin);
+      o[1] = cyc_setup; o[2] = cyc_eval; o[3] = cyc_asm; o[4] = cyc_lm; o[5] = cyc_ls;
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      o[6] = (unsigned long long)smid | ((unsigned long long)ls_steps << 32);
+      o[7] = (unsigned long long)t_begin;
+    }
+  }
+#undef LFR_TICK
+}
+
+}  // namespace lfr

@@ -142,9 +142,9 @@ void loss_eval(int kind, double sim, double s, const lfr_options& o,
 // abscissae.  The restatement builds the SAME polynomial in the normalised
 // variable t = x / h (h = largest sample step): the two constraints at 0 fix
 // the two lowest coefficients, the others come from a 2x2 (closed form) or 4x4
-// (partial pivoting) solve; the companion-matrix eigenvalues are computed as
-// the roots of the monic polynomial by an Aberth-Ehrlich iteration.
-// csrc/lfr_math.cuh mirrors this operation for operation.
+// (partial pivoting) solve; of the companion-matrix eigenvalues only the real
+// ones inside the interval can win the minimisation, and those are bracketed
+// exactly (real_roots_in).  csrc/lfr_math.cuh mirrors this operation for operation.
 // ---------------------------------------------------------------------------
 struct Sample {
   double x = 0, value = 0, gradient = 0;
@@ -157,99 +157,133 @@ double poly_eval(const double* p, int n, double x) {
   return v;
 }
 
-// Real parts of the roots of c[0..n-1] (highest degree first, n <= 5).
-// Returns the count, or -1 ("Unable to find the critical points").
-int poly_roots_real(const double* c, int n, double* out) {
+// ---- real roots of a polynomial inside an interval ---------------------------
+// MinimizePolynomial looks at the real parts of ALL roots of p', but a candidate
+// only wins if its value is strictly below the best of {middle, ends}; on an
+// interval the minimum of p is attained at an end or at a REAL critical point
+// inside it, so complex roots and roots outside [lo, hi] can never be selected.
+// The real roots inside the interval are found exactly and cheaply by
+// recursion on the derivative: between two consecutive critical points a
+// polynomial is monotone, so every sign change brackets exactly one root, which
+// a safeguarded Newton iteration (Numerical Recipes' rtsafe) then polishes.
+void horner2(const double* q, int nq, double x, double* f, double* df) {
+  double v = q[0], d = 0.0;
+  for (int i = 1; i < nq; ++i) {
+    d = d * x + v;
+    v = v * x + q[i];
+  }
+  *f = v;
+  *df = d;
+}
+
+double bracket_root(const double* q, int nq, double a, double b, double fa, double fb) {
+  if (fa == 0.0) return a;
+  if (fb == 0.0) return b;
+  double xl = fa < 0.0 ? a : b, xh = fa < 0.0 ? b : a;
+  double x = 0.5 * (a + b), dxold = std::fabs(b - a), dx = dxold, f, df;
+  horner2(q, nq, x, &f, &df);
+  for (int it = 0; it < 100; ++it) {
+    if ((((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (std::fabs(2.0 * f) > std::fabs(dxold * df))) {
+      dxold = dx;
+      dx = 0.5 * (xh - xl);
+      x = xl + dx;
+      if (xl == x) return x;
+    } else {
+      dxold = dx;
+      dx = f / df;
+      const double t = x;
+      x -= dx;
+      if (t == x) return x;
+    }
+    if (std::fabs(dx) <= 4e-16 * std::fabs(x)) return x;
+    horner2(q, nq, x, &f, &df);
+    if (f < 0.0) xl = x; else xh = x;
+  }
+  return x;
+}
+
+// Real roots of c[0..n-1] (highest degree first, degree <= 4) inside [lo, hi],
+// ascending.  Degree <= 2 uses the closed forms of Ceres' polynomial.cc.
+int real_roots_in(const double* c, int n, double lo, double hi, double* out) {
   int lead = 0;
-  while (lead + 1 < n && c[lead] == 0.0) ++lead;  // RemoveLeadingZeros
+  while (lead + 1 < n && c[lead] == 0.0) ++lead;   // RemoveLeadingZeros
   const double* p = c + lead;
   const int degree = n - lead - 1;
   if (degree <= 0) return 0;
+  int cnt = 0;
   if (degree == 1) {
-    out[0] = -p[1] / p[0];
-    return 1;
+    const double r = -p[1] / p[0];
+    if (r >= lo && r <= hi) out[cnt++] = r;
+    return cnt;
   }
-  if (degree == 2) {  // FindQuadraticPolynomialRoots
+  if (degree == 2) {  // FindQuadraticPolynomialRoots, real case
     const double a = p[0], b = p[1], cc = p[2];
     const double D = b * b - 4 * a * cc;
-    const double sq = std::sqrt(std::fabs(D));
-    if (D >= 0) {
-      if (b >= 0) {
-        out[0] = (-b - sq) / (2.0 * a);
-        out[1] = (2.0 * cc) / (-b - sq);
-      } else {
-        out[0] = (2.0 * cc) / (-b + sq);
-        out[1] = (-b + sq) / (2.0 * a);
-      }
+    if (D < 0) return 0;
+    const double sq = std::sqrt(D);
+    double r0, r1;
+    if (b >= 0) {
+      r0 = (-b - sq) / (2.0 * a);
+      r1 = (2.0 * cc) / (-b - sq);
     } else {
-      out[0] = out[1] = -b / (2.0 * a);
+      r0 = (2.0 * cc) / (-b + sq);
+      r1 = (-b + sq) / (2.0 * a);
     }
-    return 2;
+    if (r1 < r0) { const double t = r0; r0 = r1; r1 = t; }
+    if (r0 >= lo && r0 <= hi) out[cnt++] = r0;
+    if (r1 >= lo && r1 <= hi && r1 != r0) out[cnt++] = r1;
+    return cnt;
   }
-  double m[5];
-  double bound = 0.0;
-  for (int i = 0; i <= degree; ++i) {
-    m[i] = p[i] / p[0];
-    if (!std::isfinite(m[i])) return -1;
-    if (i) bound = std::max(bound, std::fabs(m[i]));
-  }
-  bound = 0.5 * (bound + 1.0);
-  static const double kCos3[3] = {0.9210609940028851, -0.79777667414035813, -0.12328431986252686};
-  static const double kSin3[3] = {0.38941834230865052, 0.60295304808712002, -0.99237139039577016};
-  static const double kCos4[4] = {0.9210609940028851, -0.38941834230865036, -0.92106099400288521,
-                                  0.38941834230865063};
-  static const double kSin4[4] = {0.38941834230865052, 0.9210609940028851, -0.3894183423086503,
-                                  -0.92106099400288499};
-  double zr[4], zi[4], wr[4], wi[4];
-  for (int i = 0; i < degree; ++i) {
-    zr[i] = bound * (degree == 3 ? kCos3[i] : kCos4[i]);
-    zi[i] = bound * (degree == 3 ? kSin3[i] : kSin4[i]);
-  }
-  for (int it = 0; it < 48; ++it) {
-    for (int i = 0; i < degree; ++i) {  // all roots from the previous iterate (Jacobi sweep)
-      double pr = m[0], pi = 0.0, dr = 0.0, di = 0.0;
-      for (int k = 1; k <= degree; ++k) {
-        const double ndr = dr * zr[i] - di * zi[i] + pr;
-        const double ndi = dr * zi[i] + di * zr[i] + pi;
-        dr = ndr;
-        di = ndi;
-        const double npr = pr * zr[i] - pi * zi[i] + m[k];
-        const double npi = pr * zi[i] + pi * zr[i];
-        pr = npr;
-        pi = npi;
-      }
-      double rr = 0.0, ri = 0.0;
-      for (int j = 0; j < degree; ++j) {
-        if (j == i) continue;
-        const double ar = zr[i] - zr[j], ai = zi[i] - zi[j];
-        const double inv = 1.0 / (ar * ar + ai * ai);
-        rr += ar * inv;
-        ri -= ai * inv;
-      }
-      wr[i] = wi[i] = 0.0;
-      if (!(pr == 0.0 && pi == 0.0)) {
-        const double inv = 1.0 / (dr * dr + di * di);
-        const double nr = (pr * dr + pi * di) * inv, ni = (pi * dr - pr * di) * inv;
-        const double qr = 1.0 - (nr * rr - ni * ri), qi = -(nr * ri + ni * rr);
-        const double inv2 = 1.0 / (qr * qr + qi * qi);
-        wr[i] = (nr * qr + ni * qi) * inv2;
-        wi[i] = (ni * qr - nr * qi) * inv2;
+  // critical points of p inside the interval (roots of p', degree - 1 <= 3)
+  double d[4], crit[3];
+  for (int i = 0; i < degree; ++i) d[i] = (degree - i) * p[i];
+  int ncrit;
+  if (degree == 3) {
+    ncrit = real_roots_in(d, 3, lo, hi, crit);
+  } else {
+    // degree 4: p' is a cubic; its critical points come from the quadratic p''
+    double dd[3], c2[2];
+    for (int i = 0; i < 3; ++i) dd[i] = (3 - i) * d[i];
+    int lead3 = 0;
+    while (lead3 + 1 < 4 && d[lead3] == 0.0) ++lead3;
+    if (lead3 > 0) {
+      ncrit = real_roots_in(d, 4, lo, hi, crit);   // degenerate cubic: closed forms above
+    } else {
+      const int n2 = real_roots_in(dd, 3, lo, hi, c2);
+      ncrit = 0;
+      double a0 = lo, f0, tmp;
+      horner2(d, 4, a0, &f0, &tmp);
+      for (int s = 0; s <= n2; ++s) {
+        const double b0 = (s < n2) ? c2[s] : hi;
+        double f1;
+        horner2(d, 4, b0, &f1, &tmp);
+        if ((f0 <= 0.0 && f1 >= 0.0) || (f0 >= 0.0 && f1 <= 0.0)) {
+          if (!(f0 == 0.0 && f1 == 0.0)) {
+            const double r = bracket_root(d, 4, a0, b0, f0, f1);
+            if (ncrit == 0 || r != crit[ncrit - 1]) crit[ncrit++] = r;
+          }
+        }
+        a0 = b0;
+        f0 = f1;
       }
     }
-    double change = 0.0;
-    for (int i = 0; i < degree; ++i) {
-      zr[i] -= wr[i];
-      zi[i] -= wi[i];
-      change = std::max(change, (wr[i] * wr[i] + wi[i] * wi[i]) /
-                                    std::max(1e-300, zr[i] * zr[i] + zi[i] * zi[i]));
+  }
+  double a0 = lo, f0, tmp;
+  horner2(p, degree + 1, a0, &f0, &tmp);
+  for (int s = 0; s <= ncrit; ++s) {
+    const double b0 = (s < ncrit) ? crit[s] : hi;
+    double f1;
+    horner2(p, degree + 1, b0, &f1, &tmp);
+    if ((f0 <= 0.0 && f1 >= 0.0) || (f0 >= 0.0 && f1 <= 0.0)) {
+      if (!(f0 == 0.0 && f1 == 0.0)) {
+        const double r = bracket_root(p, degree + 1, a0, b0, f0, f1);
+        if (cnt == 0 || r != out[cnt - 1]) out[cnt++] = r;
+      }
     }
-    if (!(change >= 1e-26)) break;
+    a0 = b0;
+    f0 = f1;
   }
-  for (int i = 0; i < degree; ++i) {
-    if (!std::isfinite(zr[i])) return -1;
-    out[i] = zr[i];
-  }
-  return degree;
+  return cnt;
 }
 
 // MinimizeInterpolatingPolynomial for the samples (0, f0, g0), (x1, f1, g1)
@@ -309,7 +343,7 @@ double hermite_minimizer(double f0, double g0, double x1, double f1, double g1, 
   double der[5], roots[4];
   const int degree = nc - 1;
   for (int i = 0; i < degree; ++i) der[i] = (degree - i) * c[i];
-  const int nr = poly_roots_real(der, degree, roots);
+  const int nr = real_roots_in(der, degree, tlo, thi, roots);
   for (int i = 0; i < nr; ++i) {
     if (roots[i] < tlo || roots[i] > thi) continue;
     v = poly_eval(c, nc, roots[i]);
@@ -1034,9 +1068,9 @@ void lfr_ref_minimize_interpolating_polynomial(const double* samples, int n, dou
                                  three ? samples[12] : 0.0, x_min, x_max, optimal_value);
 }
 
-// roots (real parts) of a polynomial given highest-degree-first (n <= 5 coefficients)
-int lfr_ref_polynomial_roots(const double* coeffs, int n, double* real_out) {
-  return poly_roots_real(coeffs, n, real_out);
+// real roots inside [lo, hi] of a polynomial given highest-degree-first (n <= 5 coefficients)
+int lfr_ref_polynomial_roots(const double* coeffs, int n, double lo, double hi, double* real_out) {
+  return real_roots_in(coeffs, n, lo, hi, real_out);
 }
 
 }  // extern "C"

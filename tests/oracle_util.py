@@ -31,7 +31,7 @@ def load_oracle():
         L.lfr_ref_minimize_interpolating_polynomial.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double,
                                                                  C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.lfr_ref_minimize_interpolating_polynomial.restype = None
-        L.lfr_ref_polynomial_roots.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.lfr_ref_polynomial_roots.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
         L.lfr_ref_polynomial_roots.restype = C.c_int
         _oracle = lib
     return _oracle

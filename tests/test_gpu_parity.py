@@ -53,9 +53,10 @@ def test_edge_eval_matches_oracle(b200, oracle):
     np.testing.assert_allclose(rhog[:, :2], rhoo[:, :2], rtol=1e-13, atol=1e-18)
 
 
-@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3"])
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3", "cfg4"])
 def test_solve_matches_oracle(b200, oracle, cfg):
-    """BASELINE.json configs[0..2] at full size."""
+    """BASELINE.json configs[0..3] at full size (cfg4 on one GPU here; its 4-GPU
+    sharding is covered by the dist tests)."""
     _, p = get_problem(cfg)
     err, st = _compare(b200, oracle, p)
     print(cfg, "max err %.3e units" % err, "iters", st["total_iterations"], "kernel ms", st["kernel_ms"])
@@ -92,6 +93,19 @@ def test_line_search_contraction_path(b200, oracle):
     assert st_g["total_line_search_steps"] == st_o["total_line_search_steps"]
     assert np.abs(pos_g - pos_o).max() <= TOL_UNITS
     np.testing.assert_array_equal(st_g["iterations"], st_o["iterations"])
+
+
+def test_duplicate_pairs_take_the_serial_assembly_path(b200, oracle):
+    """A pair listed twice duplicates every edge of its matches: the edge/twin
+    pairing of the fast assembly does not hold and the kernel must fall back to
+    its serial path, with the same answer as the oracle."""
+    from lfr_b200 import MatchSet, build_problem, synth
+    ms = synth.generate("cfg1", seed=21)
+    dup = ms.select_pairs(np.array([0]))
+    both = MatchSet.concatenate([ms, dup])
+    p = build_problem(both)
+    assert p.graph.n_edges == 2 * (ms.n_matches + dup.n_matches)
+    _compare(b200, oracle, p)
 
 
 def test_plan_resolve_is_deterministic(b200):

@@ -155,13 +155,17 @@ def test_quintic_interpolation_and_roots(oracle):
     assert abs(v - p(x)) < 1e-12
     out = np.zeros(8)
     co = np.array([1.0, -6.0, 11.0, -6.0])           # (x-1)(x-2)(x-3)
-    n = oracle.lib.lfr_ref_polynomial_roots(co.ctypes.data, 4, out.ctypes.data)
+    n = oracle.lib.lfr_ref_polynomial_roots(co.ctypes.data, 4, 0.0, 10.0, out.ctypes.data)
     assert n == 3
-    np.testing.assert_allclose(sorted(out[:3]), [1, 2, 3], atol=1e-10)
-    co = np.array([1.0, 0.0, 0.0, 0.0, 4.0])         # x^4 + 4: roots +-1 +- i
-    n = oracle.lib.lfr_ref_polynomial_roots(co.ctypes.data, 5, out.ctypes.data)
+    np.testing.assert_allclose(out[:3], [1, 2, 3], rtol=1e-14)
+    n = oracle.lib.lfr_ref_polynomial_roots(co.ctypes.data, 4, 1.5, 2.5, out.ctypes.data)
+    assert n == 1 and abs(out[0] - 2) < 1e-14
+    co = np.array([1.0, 0.0, 0.0, 0.0, 4.0])         # x^4 + 4: no real root
+    assert oracle.lib.lfr_ref_polynomial_roots(co.ctypes.data, 5, -10.0, 10.0, out.ctypes.data) == 0
+    co = np.poly([0.1, 0.35, 0.36, 0.9])              # quartic with two close roots
+    n = oracle.lib.lfr_ref_polynomial_roots(np.ascontiguousarray(co).ctypes.data, 5, 0.0, 1.0, out.ctypes.data)
     assert n == 4
-    np.testing.assert_allclose(sorted(out[:4]), [-1, -1, 1, 1], atol=1e-10)
+    np.testing.assert_allclose(out[:4], [0.1, 0.35, 0.36, 0.9], rtol=1e-10)
 
 
 def _two_node_problem(t, sim=0.9):
