@@ -156,20 +156,29 @@ def run_reference(args):
     from oracle_util import load_oracle
     orc = load_oracle()
     cores = os.cpu_count() or 1
-    p, n_tracks = build_workload(args.workload)
+    # the B200 arm at --gpus N solves N scenes (one per GPU, weak scaling): same work here
+    from lfr_b200 import synth
+    base_seed = synth.CONFIGS[synth.ALIASES.get(args.workload, args.workload)].seed
+    scenes = [build_workload(args.workload, seed=(base_seed + 7919 * r) if args.gpus > 1 else None)
+              for r in range(max(1, args.gpus))]
+    p, n_tracks = scenes[0]
+    n_tracks = sum(t for _, t in scenes)
     o = orc.default_options(n_threads=cores)
     t_w = time.perf_counter()
     n_w = 0
     while n_w < max(args.warmup, 3) or time.perf_counter() - t_w < 1.5:   # host threads / clocks settle
-        orc.solve(p, o)
+        for q, _ in scenes:
+            orc.solve(q, o)
         n_w += 1
     t = []
     iters = 0
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        _, st = orc.solve(p, o)
+        iters = 0
+        for q, _ in scenes:
+            _, st = orc.solve(q, o)
+            iters += st["total_iterations"]
         t.append(time.perf_counter() - t0)
-        iters = st["total_iterations"]
     ms = 1e3 * float(np.mean(t))
     value = n_tracks / (ms / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -240,6 +249,7 @@ def run_b200(args):
     stt, bufs = lib.make_stats(p.n_components)
     d2h = 16 * p.graph.n_nodes + 8 * p.n_components
     e2e_t = []
+    e2e_parts = []
     for i in range(args.warmup + args.steps):
         pos_pinned.zero_()
         flush.zero_()
@@ -251,7 +261,9 @@ def run_b200(args):
         lib.check(rc, "lfr_solve")
         if i >= args.warmup:
             e2e_t.append(dt)
+            e2e_parts.append((stt.h2d_ms, stt.kernel_ms, stt.d2h_ms))
     e2e_ms = 1e3 * float(np.mean(e2e_t))
+    e2e_break = [float(x) for x in np.mean(np.array(e2e_parts), axis=0)]
     clocks = sampler.stop() if sampler else None
     # ---- reduce over ranks --------------------------------------------------------------------
     tot_tracks, tot_iters, tot_alg = n_tracks, int(st["total_iterations"]), alg_bytes
@@ -294,7 +306,8 @@ def run_b200(args):
         "lm_iters_per_s": tot_iters / (ms_per_step / 1e3),
         "e2e": {"value": tot_tracks / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "api": "lfr_solve() (include/lfr.h) with pinned host buffers"},
+                "api": "lfr_solve() (include/lfr.h) with pinned host buffers",
+                "stages_ms": {"h2d_and_schedule": e2e_break[0], "kernels": e2e_break[1], "d2h": e2e_break[2]}},
         "gpu_launches": int(launches * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(),

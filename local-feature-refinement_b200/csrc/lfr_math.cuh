@@ -152,7 +152,7 @@ __device__ __forceinline__ void horner2(const double* q, int nq, double x, doubl
   *df = d;
 }
 
-__device__ __noinline__ double bracket_root(const double* q, int nq, double a, double b, double fa, double fb) {
+__device__ __forceinline__ double bracket_root(const double* q, int nq, double a, double b, double fa, double fb) {
   if (fa == 0.0) return a;
   if (fb == 0.0) return b;
   double xl = fa < 0.0 ? a : b, xh = fa < 0.0 ? b : a;
@@ -178,9 +178,37 @@ __device__ __noinline__ double bracket_root(const double* q, int nq, double a, d
   return x;
 }
 
-// Real roots of c[0..n-1] (highest degree first, degree <= 4) inside [lo, hi],
-// ascending.  Degree <= 2 uses the closed forms of Ceres' polynomial.cc.
-__device__ __noinline__ int real_roots_in(const double* c, int n, double lo, double hi, double* out) {
+// Roots of q (nq coefficients) in the segments cut out of [lo, hi] by its sorted
+// critical points brk[0..nbrk) (nbrk <= 3): q is monotone on each segment, so a
+// sign change brackets exactly one root.  One segment per lane; the results are
+// gathered in segment order (ascending), dropping repeats.
+__device__ __forceinline__ int segment_roots(const double* q, int nq, double b0, double b1, double b2, int nbrk,
+                                             double lo, double hi, double* out, int lane) {
+  bool has = false;
+  double r = 0.0;
+  if (lane <= nbrk) {
+    const double lefts[4] = {lo, b0, b1, b2};
+    const double xa = lane == 0 ? lefts[0] : (lane == 1 ? lefts[1] : (lane == 2 ? lefts[2] : lefts[3]));
+    const double inner = lane == 0 ? b0 : (lane == 1 ? b1 : b2);
+    const double xb = (lane < nbrk) ? inner : hi;
+    double fa, fb, tmp;
+    horner2(q, nq, xa, &fa, &tmp);
+    horner2(q, nq, xb, &fb, &tmp);
+    has = ((fa <= 0.0 && fb >= 0.0) || (fa >= 0.0 && fb <= 0.0)) && !(fa == 0.0 && fb == 0.0);
+    if (has) r = bracket_root(q, nq, xa, xb, fa, fb);
+  }
+  int cnt = 0;
+  for (int s = 0; s <= nbrk; ++s) {
+    const int hs = __shfl_sync(0xffffffffu, (int)has, s);
+    const double rs = __shfl_sync(0xffffffffu, r, s);
+    if (hs && (cnt == 0 || rs != out[cnt - 1])) out[cnt++] = rs;
+  }
+  return cnt;
+}
+
+// Real roots inside [lo, hi] of a polynomial of degree <= 3, ascending.
+// Degree <= 2: the closed forms of Ceres' polynomial.cc.
+__device__ __forceinline__ int roots_upto3(const double* c, int n, double lo, double hi, double* out, int lane) {
   int lead = 0;
   while (lead + 1 < n && c[lead] == 0.0) ++lead;   // RemoveLeadingZeros
   const double* p = c + lead;
@@ -210,56 +238,22 @@ __device__ __noinline__ int real_roots_in(const double* c, int n, double lo, dou
     if (r1 >= lo && r1 <= hi && r1 != r0) out[cnt++] = r1;
     return cnt;
   }
-  // critical points of p inside the interval (roots of p', degree - 1 <= 3)
-  double d[4], crit[3];
-  for (int i = 0; i < degree; ++i) d[i] = (degree - i) * p[i];
-  int ncrit;
-  if (degree == 3) {
-    ncrit = real_roots_in(d, 3, lo, hi, crit);
-  } else {
-    // degree 4: p' is a cubic; its critical points come from the quadratic p''
-    double dd[3], c2[2];
-    for (int i = 0; i < 3; ++i) dd[i] = (3 - i) * d[i];
-    int lead3 = 0;
-    while (lead3 + 1 < 4 && d[lead3] == 0.0) ++lead3;
-    if (lead3 > 0) {
-      ncrit = real_roots_in(d, 4, lo, hi, crit);   // degenerate cubic: closed forms above
-    } else {
-      const int n2 = real_roots_in(dd, 3, lo, hi, c2);
-      ncrit = 0;
-      double a0 = lo, f0, tmp;
-      horner2(d, 4, a0, &f0, &tmp);
-      for (int s = 0; s <= n2; ++s) {
-        const double b0 = (s < n2) ? c2[s] : hi;
-        double f1;
-        horner2(d, 4, b0, &f1, &tmp);
-        if ((f0 <= 0.0 && f1 >= 0.0) || (f0 >= 0.0 && f1 <= 0.0)) {
-          if (!(f0 == 0.0 && f1 == 0.0)) {
-            const double r = bracket_root(d, 4, a0, b0, f0, f1);
-            if (ncrit == 0 || r != crit[ncrit - 1]) crit[ncrit++] = r;
-          }
-        }
-        a0 = b0;
-        f0 = f1;
-      }
-    }
-  }
-  double a0 = lo, f0, tmp;
-  horner2(p, degree + 1, a0, &f0, &tmp);
-  for (int s = 0; s <= ncrit; ++s) {
-    const double b0 = (s < ncrit) ? crit[s] : hi;
-    double f1;
-    horner2(p, degree + 1, b0, &f1, &tmp);
-    if ((f0 <= 0.0 && f1 >= 0.0) || (f0 >= 0.0 && f1 <= 0.0)) {
-      if (!(f0 == 0.0 && f1 == 0.0)) {
-        const double r = bracket_root(p, degree + 1, a0, b0, f0, f1);
-        if (cnt == 0 || r != out[cnt - 1]) out[cnt++] = r;
-      }
-    }
-    a0 = b0;
-    f0 = f1;
-  }
-  return cnt;
+  const double d[3] = {3.0 * p[0], 2.0 * p[1], p[2]};  // critical points of the cubic
+  double crit[2] = {0.0, 0.0};
+  const int ncrit = roots_upto3(d, 3, lo, hi, crit, lane);
+  return segment_roots(p, 4, crit[0], crit[1], 0.0, ncrit, lo, hi, out, lane);
+}
+
+// Real roots of c[0..n-1] (highest degree first, degree <= 4) inside [lo, hi], ascending.
+__device__ __noinline__ int real_roots_in(const double* c, int n, double lo, double hi, double* out, int lane) {
+  int lead = 0;
+  while (lead + 1 < n && c[lead] == 0.0) ++lead;
+  if (n - lead - 1 <= 3) return roots_upto3(c + lead, n - lead, lo, hi, out, lane);
+  const double* p = c + lead;  // quartic
+  const double d[4] = {4.0 * p[0], 3.0 * p[1], 2.0 * p[2], p[3]};
+  double crit[3] = {0.0, 0.0, 0.0};
+  const int ncrit = roots_upto3(d, 4, lo, hi, crit, lane);
+  return segment_roots(p, 5, crit[0], crit[1], crit[2], ncrit, lo, hi, out, lane);
 }
 
 // Minimiser over [lo, hi] (in x) of the Hermite interpolant through (0, f0, g0),
@@ -335,7 +329,7 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
   double der[5], roots[4];
   const int degree = nc - 1;
   for (int i = 0; i < degree; ++i) der[i] = (degree - i) * c[i];
-  const int nr = real_roots_in(der, degree, tlo, thi, roots);
+  const int nr = real_roots_in(der, degree, tlo, thi, roots, lane);
   for (int i = 0; i < nr; ++i) {
     if (roots[i] < tlo || roots[i] > thi) continue;
     v = poly_eval(c, nc, roots[i]);

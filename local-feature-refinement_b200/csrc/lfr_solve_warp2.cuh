@@ -271,38 +271,34 @@ __device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const
   // holds the current pivot column and ONE compact loop body serves every column
   // (a fully unrolled elimination is ~100 KB of straight-line code and stalls on
   // instruction fetch).
-  // Pivot rows are left un-normalised (the pivot lane only has to publish its
-  // registers), every lane scales its own multiplier with the published
-  // reciprocal, and the reciprocal of the NEXT pivot is computed by all lanes
-  // right after the first update of the step, in the shadow of the remaining
-  // ones: the dependent chain of a step is STS -> LDS -> DMUL -> DFMA.
-  double rp = 1.0 / a[0], myrp = 1.0;
   for (int j = 0; j < n; ++j) {
     const int m = n - j;  // live columns j .. n-1 sit in slots 0 .. m-1
     double* buf = C.prow + (j & 1) * C.prow_stride;
     if (i == j) {
-      myrp = rp;
-      buf[NREG + 1] = rp;
-      buf[NREG + 2] = a[0];
+      const double piv = a[0];
+      const double rp = 1.0 / piv;
+      buf[NREG + 1] = piv;
 #pragma unroll
       for (int k = 1; k < NREG; ++k) {
-        if (k < m) buf[k] = a[k];
+        if (k < m) {
+          a[k] *= rp;
+          buf[k] = a[k];
+        }
       }
+      b *= rp;
       buf[NREG] = b;
     }
     __syncwarp();
-    const double f = (i == j) ? 0.0 : a[0] * buf[NREG + 1];  // the pivot row itself is kept
-    if (1 < m) a[0] = a[1] - f * buf[1];
-    rp = 1.0 / a[0];  // look-ahead: meaningful in lane j + 1
+    const double piv = buf[NREG + 1];
+    ok = ok && (piv > 0.0) && isfinite(piv);
+    const double f = (i == j) ? 0.0 : a[0];  // the pivot row itself is kept
 #pragma unroll
-    for (int k = 2; k < NREG; ++k) {
+    for (int k = 1; k < NREG; ++k) {
       if (k < m) a[k - 1] = a[k] - f * buf[k];
     }
     b -= f * buf[NREG];
-    const double piv = buf[NREG + 2];
-    ok = ok && (piv > 0.0) && isfinite(piv);
   }
-  const double y = b * myrp;  // row i now reads  piv_i * y_i = b_i
+  const double y = b;  // rows are normalised: the right-hand side is the solution
   double mc = 0.0, dot = 0.0, mx = 0.0;
   bool finite = true;
   if (act) {
@@ -370,7 +366,7 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
 
   const bool prof = (P.st_cycles != nullptr);
   long long t_begin = prof ? clock64() : 0, t_mark = t_begin;
-  long long cyc_eval = 0, cyc_asm = 0, cyc_lm = 0, cyc_ls = 0, cyc_setup = 0;
+  long long cyc_eval = 0, cyc_asm = 0, cyc_lm = 0, cyc_ls = 0, cyc_setup = 0, cyc_poly = 0;
 #define LFR_TICK(acc) do { if (prof) { const long long now__ = clock64(); acc += now__ - t_mark; t_mark = now__; } } while (0)
 
   // ---- component setup (solve.cc:98-143) --------------------------------------
@@ -565,7 +561,9 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
         ++ls_iter;
         ++ls_steps;
         if (ls_iter >= K.max_ls_iter) break;
+        LFR_TICK(cyc_ls);
         const double step = ls_next_step(initial, previous, current, K, lane);
+        LFR_TICK(cyc_poly);
         if (step * dmax < K.ls_min_step) break;
         previous = current;
         make_candidate2(C, step, K);
@@ -635,7 +633,7 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       o[6] = (unsigned long long)smid | ((unsigned long long)ls_steps << 32);
-      o[7] = (unsigned long long)t_begin;
+      o[7] = (unsigned long long)cyc_poly;
     }
   }
 #undef LFR_TICK

@@ -202,11 +202,30 @@ double bracket_root(const double* q, int nq, double a, double b, double fa, doub
   return x;
 }
 
-// Real roots of c[0..n-1] (highest degree first, degree <= 4) inside [lo, hi],
-// ascending.  Degree <= 2 uses the closed forms of Ceres' polynomial.cc.
-int real_roots_in(const double* c, int n, double lo, double hi, double* out) {
+// Roots of q in the segments cut out of [lo, hi] by its sorted critical points
+// brk[0..nbrk): q is monotone on each segment, so a sign change brackets exactly
+// one root.  (The CUDA path runs the segments on separate lanes.)
+int segment_roots(const double* q, int nq, const double* brk, int nbrk, double lo, double hi, double* out) {
+  int cnt = 0;
+  for (int s = 0; s <= nbrk; ++s) {
+    const double xa = (s == 0) ? lo : brk[s - 1];
+    const double xb = (s < nbrk) ? brk[s] : hi;
+    double fa, fb, tmp;
+    horner2(q, nq, xa, &fa, &tmp);
+    horner2(q, nq, xb, &fb, &tmp);
+    const bool has = ((fa <= 0.0 && fb >= 0.0) || (fa >= 0.0 && fb <= 0.0)) && !(fa == 0.0 && fb == 0.0);
+    if (!has) continue;
+    const double r = bracket_root(q, nq, xa, xb, fa, fb);
+    if (cnt == 0 || r != out[cnt - 1]) out[cnt++] = r;
+  }
+  return cnt;
+}
+
+// Real roots inside [lo, hi] of a polynomial of degree <= 3, ascending.
+// Degree <= 2: the closed forms of Ceres' polynomial.cc.
+int roots_upto3(const double* c, int n, double lo, double hi, double* out) {
   int lead = 0;
-  while (lead + 1 < n && c[lead] == 0.0) ++lead;   // RemoveLeadingZeros
+  while (lead + 1 < n && c[lead] == 0.0) ++lead;  // RemoveLeadingZeros
   const double* p = c + lead;
   const int degree = n - lead - 1;
   if (degree <= 0) return 0;
@@ -229,61 +248,27 @@ int real_roots_in(const double* c, int n, double lo, double hi, double* out) {
       r0 = (2.0 * cc) / (-b + sq);
       r1 = (-b + sq) / (2.0 * a);
     }
-    if (r1 < r0) { const double t = r0; r0 = r1; r1 = t; }
+    if (r1 < r0) std::swap(r0, r1);
     if (r0 >= lo && r0 <= hi) out[cnt++] = r0;
     if (r1 >= lo && r1 <= hi && r1 != r0) out[cnt++] = r1;
     return cnt;
   }
-  // critical points of p inside the interval (roots of p', degree - 1 <= 3)
-  double d[4], crit[3];
-  for (int i = 0; i < degree; ++i) d[i] = (degree - i) * p[i];
-  int ncrit;
-  if (degree == 3) {
-    ncrit = real_roots_in(d, 3, lo, hi, crit);
-  } else {
-    // degree 4: p' is a cubic; its critical points come from the quadratic p''
-    double dd[3], c2[2];
-    for (int i = 0; i < 3; ++i) dd[i] = (3 - i) * d[i];
-    int lead3 = 0;
-    while (lead3 + 1 < 4 && d[lead3] == 0.0) ++lead3;
-    if (lead3 > 0) {
-      ncrit = real_roots_in(d, 4, lo, hi, crit);   // degenerate cubic: closed forms above
-    } else {
-      const int n2 = real_roots_in(dd, 3, lo, hi, c2);
-      ncrit = 0;
-      double a0 = lo, f0, tmp;
-      horner2(d, 4, a0, &f0, &tmp);
-      for (int s = 0; s <= n2; ++s) {
-        const double b0 = (s < n2) ? c2[s] : hi;
-        double f1;
-        horner2(d, 4, b0, &f1, &tmp);
-        if ((f0 <= 0.0 && f1 >= 0.0) || (f0 >= 0.0 && f1 <= 0.0)) {
-          if (!(f0 == 0.0 && f1 == 0.0)) {
-            const double r = bracket_root(d, 4, a0, b0, f0, f1);
-            if (ncrit == 0 || r != crit[ncrit - 1]) crit[ncrit++] = r;
-          }
-        }
-        a0 = b0;
-        f0 = f1;
-      }
-    }
-  }
-  double a0 = lo, f0, tmp;
-  horner2(p, degree + 1, a0, &f0, &tmp);
-  for (int s = 0; s <= ncrit; ++s) {
-    const double b0 = (s < ncrit) ? crit[s] : hi;
-    double f1;
-    horner2(p, degree + 1, b0, &f1, &tmp);
-    if ((f0 <= 0.0 && f1 >= 0.0) || (f0 >= 0.0 && f1 <= 0.0)) {
-      if (!(f0 == 0.0 && f1 == 0.0)) {
-        const double r = bracket_root(p, degree + 1, a0, b0, f0, f1);
-        if (cnt == 0 || r != out[cnt - 1]) out[cnt++] = r;
-      }
-    }
-    a0 = b0;
-    f0 = f1;
-  }
-  return cnt;
+  const double d[3] = {3.0 * p[0], 2.0 * p[1], p[2]};  // critical points of the cubic
+  double crit[2] = {0.0, 0.0};
+  const int ncrit = roots_upto3(d, 3, lo, hi, crit);
+  return segment_roots(p, 4, crit, ncrit, lo, hi, out);
+}
+
+// Real roots of c[0..n-1] (highest degree first, degree <= 4) inside [lo, hi], ascending.
+int real_roots_in(const double* c, int n, double lo, double hi, double* out) {
+  int lead = 0;
+  while (lead + 1 < n && c[lead] == 0.0) ++lead;
+  if (n - lead - 1 <= 3) return roots_upto3(c + lead, n - lead, lo, hi, out);
+  const double* p = c + lead;  // quartic
+  const double d[4] = {4.0 * p[0], 3.0 * p[1], 2.0 * p[2], p[3]};
+  double crit[3] = {0.0, 0.0, 0.0};
+  const int ncrit = roots_upto3(d, 4, lo, hi, crit);
+  return segment_roots(p, 5, crit, ncrit, lo, hi, out);
 }
 
 // MinimizeInterpolatingPolynomial for the samples (0, f0, g0), (x1, f1, g1)

@@ -47,7 +47,4 @@ w = np.argsort(-tot)[:8]
 idx = np.nonzero(sel)[0][w]
 for i in idx:
     print("  slot", i, "nodes", int(p.comp_ptr[i + 1] - p.comp_ptr[i]), "iters", it[i],
-          "ls_steps", int(cyc[i, 6]) >> 32, "cycles", cyc[i, :6].tolist(), "sm", int(cyc[i, 6]) & 0xffffffff)
-t0 = cyc[sel, 7].astype(np.float64)
-t1 = t0 + tot
-print("span (max end - min start) cycles: %.0f" % (t1.max() - t0.min()))
+          "ls_steps", int(cyc[i, 6]) >> 32, "cycles", cyc[i, :6].tolist(), "poly", int(cyc[i, 7]), "sm", int(cyc[i, 6]) & 0xffffffff)
