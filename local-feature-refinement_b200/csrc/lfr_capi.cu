@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "lfr_solve_cta.cuh"
 #include "lfr_solve_warp2.cuh"
 
 namespace {
@@ -135,6 +136,11 @@ struct lfr_plan {
   std::vector<Bucket> buckets;
   std::vector<uint32_t> comp_size;  // nodes per dispatch slot
   std::vector<uint32_t> list_host;
+  // CTA tier (block-Jacobi PCG): components with more than kMaxWarpN2 unknowns, or all with linear_solver = 2
+  std::vector<uint32_t> large_slots;
+  uint32_t n_large = 0;
+  DevBuf L_comps, L_eidx, L_meta, L_inlist, L_scr, L_q, L_node, L_outptr, L_inptr, L_freeof, L_x, L_xc, L_lof, L_vec;
+  uint64_t L_total_free = 0;
   uint32_t n_solved = 0;
   bool profile = false;
   cudaStream_t streams[kMaxStreams] = {};
@@ -171,7 +177,9 @@ void free_plan(lfr_plan* pl) {
   if (!pl) return;
   DevBuf* bufs[] = {&pl->row_ptr, &pl->edges, &pl->track, &pl->comp, &pl->is_root, &pl->comp_ptr, &pl->comp_nodes,
                     &pl->local_of, &pl->pos, &pl->pos_init, &pl->iter, &pl->term, &pl->cost0, &pl->cost1, &pl->ls,
-                    &pl->kept, &pl->cycles, &pl->lists, &pl->err};
+                    &pl->kept, &pl->cycles, &pl->lists, &pl->err, &pl->L_comps, &pl->L_eidx, &pl->L_meta,
+                    &pl->L_inlist, &pl->L_scr, &pl->L_q, &pl->L_node, &pl->L_outptr, &pl->L_inptr, &pl->L_freeof,
+                    &pl->L_x, &pl->L_xc, &pl->L_lof, &pl->L_vec};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < pl->n_streams; ++i) {
     if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
@@ -203,6 +211,8 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   pl->buckets.clear();
   pl->list_host.clear();
   const bool force_v1 = getenv("LFR_FORCE_V1") != nullptr;
+  const bool force_pcg = pl->opt.linear_solver == 2;
+  pl->large_slots.clear();
   for (uint32_t c = 0; c < p->n_components; ++c) {
     const uint32_t beg = p->comp_ptr[c], end = p->comp_ptr[c + 1];
     if (end < beg || end > pl->total_slots) return fail(LFR_EINVAL, "comp_ptr not monotone");
@@ -220,11 +230,10 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       nfree += p->is_root[v] ? 0 : 1;
     }
     const int n2 = std::max(2 * (int)nfree, 2);
-    if (n2 > lfr::kMaxWarpN2 || nc > (uint32_t)lfr::kMaxWarpNodes || eup > 65535) {
-      char buf[160];
-      snprintf(buf, sizeof buf, "component %u (nodes=%u, unknowns=%d, out-edges=%llu) exceeds the warp-tier caps",
-               c, nc, n2, (unsigned long long)eup);
-      return fail(LFR_EUNSUPPORTED, buf);
+    if (force_pcg || n2 > lfr::kMaxWarpN2 || nc > (uint32_t)lfr::kMaxWarpNodes || eup > 65535) {
+      if (nc > 16383) return fail(LFR_EUNSUPPORTED, "component with more than 16383 nodes");
+      pl->large_slots.push_back(c);
+      continue;
     }
     const int e = std::max<int>(1, (int)eup);
     int vi = (n2 <= 16) ? 0 : (n2 <= 32 ? 1 : 2);
@@ -256,6 +265,100 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       pl->buckets.push_back(b);
     }
   }
+  return LFR_OK;
+}
+
+// Host-side preparation of the CTA-tier components (solve.cc:98-143 for each):
+// kept-edge lists with local indices and loss kinds, in-edge lists, free-variable
+// numbering.  These are the few components too large for one warp.
+int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
+  pl->n_large = (uint32_t)pl->large_slots.size();
+  pl->L_total_free = 0;
+  if (pl->n_large == 0) return LFR_OK;
+  std::vector<lfr::CtaComp> comps(pl->n_large);
+  std::vector<uint32_t> eidx, meta, inlist, node, outptr, inptr, lof;
+  std::vector<int32_t> freeof;
+  std::vector<int32_t> local(p->n_nodes, -1);
+  uint64_t e_off = 0, n_off = 0, f_off = 0;
+  for (uint32_t k = 0; k < pl->n_large; ++k) {
+    const uint32_t c = pl->large_slots[k];
+    const uint32_t beg = p->comp_ptr[c], nc = p->comp_ptr[c + 1] - beg;
+    for (uint32_t l = 0; l < nc; ++l) local[p->comp_nodes[beg + l]] = (int32_t)l;
+    const size_t e0 = eidx.size();
+    std::vector<uint32_t> cin(nc, 0), cout(nc, 0);
+    outptr.push_back(0);
+    for (uint32_t l = 0; l < nc; ++l) {
+      const uint32_t v = p->comp_nodes[beg + l];
+      node.push_back(v);
+      for (uint32_t e = p->row_ptr[v]; e < p->row_ptr[v + 1]; ++e) {
+        const uint32_t dst = p->edges[e].dst;
+        if (dst >= p->n_nodes || dst == v) return fail(LFR_EINVAL, "edge with dst out of range or a self edge");
+        uint32_t kind;
+        if (p->track[v] == p->track[dst]) kind = LFR_EDGE_CAUCHY;        // solve.cc:105
+        else if (p->comp[v] == p->comp[dst]) kind = LFR_EDGE_TUKEY;      // solve.cc:114
+        else continue;                                                   // solve.cc:123
+        if (p->is_root[v] && p->is_root[dst]) continue;                  // all-constant block (A.1)
+        const int32_t dl = local[dst];
+        if (dl < 0) return fail(LFR_EINVAL, "component_idx and nodes_in_component disagree");
+        eidx.push_back(e);
+        meta.push_back(l | ((uint32_t)dl << 14) | (kind << 28));
+        ++cout[l];
+        ++cin[dl];
+      }
+      outptr.push_back((uint32_t)(eidx.size() - e0));
+    }
+    const uint32_t ec = (uint32_t)(eidx.size() - e0);
+    // in-edge lists: counting sort by destination (stable => ascending edge index)
+    std::vector<uint32_t> ip(nc + 1, 0);
+    for (uint32_t l = 0; l < nc; ++l) ip[l + 1] = ip[l] + cin[l];
+    std::vector<uint32_t> fill(ip.begin(), ip.end() - 1);
+    inlist.resize(e0 + ec);
+    for (uint32_t j = 0; j < ec; ++j) {
+      const uint32_t dl = (meta[e0 + j] >> 14) & 0x3fff;
+      inlist[e0 + fill[dl]++] = j;
+    }
+    inptr.insert(inptr.end(), ip.begin(), ip.end());
+    uint32_t nf = 0;
+    for (uint32_t l = 0; l < nc; ++l) {
+      const bool is_free = (cout[l] + cin[l] > 0) && !p->is_root[p->comp_nodes[beg + l]];
+      freeof.push_back(is_free ? (int32_t)nf : -1);
+      if (is_free) {
+        lof.push_back(l);
+        ++nf;
+      }
+    }
+    for (uint32_t l = 0; l < nc; ++l) local[p->comp_nodes[beg + l]] = -1;
+    lfr::CtaComp& cc = comps[k];
+    cc.slot = c;
+    cc.Nc = nc;
+    cc.Ec = ec;
+    cc.nf = nf;
+    cc.e_off = e_off;
+    cc.n_off = n_off;
+    cc.f_off = f_off;
+    cc.comp_index = k;
+    cc.pad = 0;
+    e_off += ec;
+    n_off += nc;
+    f_off += nf;
+  }
+  pl->L_total_free = f_off;
+  LFR_TRY(upload(&pl->L_comps, comps.data(), comps.size(), s));
+  LFR_TRY(upload(&pl->L_eidx, eidx.data(), eidx.size(), s));
+  LFR_TRY(upload(&pl->L_meta, meta.data(), meta.size(), s));
+  LFR_TRY(upload(&pl->L_inlist, inlist.data(), inlist.size(), s));
+  LFR_TRY(upload(&pl->L_node, node.data(), node.size(), s));
+  LFR_TRY(upload(&pl->L_outptr, outptr.data(), outptr.size(), s));
+  LFR_TRY(upload(&pl->L_inptr, inptr.data(), inptr.size(), s));
+  LFR_TRY(upload(&pl->L_freeof, freeof.data(), freeof.size(), s));
+  LFR_TRY(upload(&pl->L_lof, lof.data(), lof.size(), s));
+  LFR_TRY(pl->L_scr.reserve(sizeof(double) * 7 * std::max<uint64_t>(e_off, 1)));
+  LFR_TRY(pl->L_q.reserve(sizeof(double) * 2 * std::max<uint64_t>(e_off, 1)));
+  LFR_TRY(pl->L_x.reserve(sizeof(double) * 2 * std::max<uint64_t>(n_off, 1)));
+  LFR_TRY(pl->L_xc.reserve(sizeof(double) * 2 * std::max<uint64_t>(n_off, 1)));
+  LFR_TRY(pl->L_vec.reserve(sizeof(double) * (2 * lfr::V_COUNT + 6) * std::max<uint64_t>(f_off, 1)));
+  // the upload sources above are locals: make sure the copies are done before they go away
+  LFR_CUDA(cudaStreamSynchronize(s));
   return LFR_OK;
 }
 
@@ -302,6 +405,7 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
   else
     LFR_CUDA(cudaMemsetAsync(pl->pos_init.p, 0, sizeof(double) * 2 * N, s));
   LFR_TRY(build_buckets(pl, p));  // host work overlaps the copies above
+  LFR_TRY(prepare_large(pl, p, s));
   LFR_TRY(upload(&pl->lists, pl->list_host.data(), pl->list_host.size(), s));
   if (pl->total_slots) {
     lfr::local_index_kernel<<<(pl->total_slots + 255) / 256, 256, 0, s>>>(
@@ -310,7 +414,7 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
     LFR_CUDA(cudaGetLastError());
   }
   // streams for concurrent bucket launches
-  const int want = std::min<int>(kMaxStreams, std::max<int>(0, (int)pl->buckets.size() - 1));
+  const int want = std::min<int>(kMaxStreams, std::max<int>(0, (int)pl->buckets.size() - 1 + (pl->n_large ? 1 : 0)));
   if (!pl->ev_fork) LFR_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
   while (pl->n_streams < want) {
     LFR_CUDA(cudaStreamCreateWithFlags(&pl->streams[pl->n_streams], cudaStreamNonBlocking));
@@ -346,13 +450,39 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
                              cudaMemcpyDeviceToDevice, s));
   const lfr::DevProblem P = pl->dev();
   const int nb = (int)pl->buckets.size();
-  if (nb > 1) LFR_CUDA(cudaEventRecord(pl->ev_fork, s));
+  const int n_side = std::max(0, nb - 1) + ((pl->n_large && nb > 0) ? 1 : 0);
+  if (n_side > 0) LFR_CUDA(cudaEventRecord(pl->ev_fork, s));
+  int side = 0;
+  if (pl->n_large) {  // the CTA tier first: its components are the longest
+    cudaStream_t bs = s;
+    if (nb > 0) {
+      bs = pl->streams[side++ % pl->n_streams];
+      LFR_CUDA(cudaStreamWaitEvent(bs, pl->ev_fork, 0));
+    }
+    lfr::CtaArrays A;
+    A.eidx = pl->L_eidx.as<uint32_t>();
+    A.meta = pl->L_meta.as<uint32_t>();
+    A.inlist = pl->L_inlist.as<uint32_t>();
+    A.scr = pl->L_scr.as<double>();
+    A.q = pl->L_q.as<double>();
+    A.node = pl->L_node.as<uint32_t>();
+    A.outptr = pl->L_outptr.as<uint32_t>();
+    A.inptr = pl->L_inptr.as<uint32_t>();
+    A.freeof = pl->L_freeof.as<int32_t>();
+    A.x = pl->L_x.as<double>();
+    A.xc = pl->L_xc.as<double>();
+    A.lof = pl->L_lof.as<uint32_t>();
+    A.vec = pl->L_vec.as<double>();
+    A.total_free = pl->L_total_free;
+    lfr::solve_cta_kernel<<<pl->n_large, lfr::kCtaThreads, 0, bs>>>(P, pl->K, A, pl->L_comps.as<lfr::CtaComp>());
+    LFR_CUDA(cudaGetLastError());
+  }
   for (int i = 0; i < nb; ++i) {
     const Bucket& b = pl->buckets[i];
     // bucket 0 runs on the caller's stream, the others on side streams forked from it
     cudaStream_t bs = s;
     if (i > 0) {
-      bs = pl->streams[(i - 1) % pl->n_streams];
+      bs = pl->streams[side++ % pl->n_streams];
       LFR_CUDA(cudaStreamWaitEvent(bs, pl->ev_fork, 0));
     }
     lfr::WarpBucket wb;
@@ -376,7 +506,7 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
       lfr::solve_warp_kernel<1><<<grid, 32, smem, bs>>>(P, pl->K, wb);
     LFR_CUDA(cudaGetLastError());
   }
-  for (int k = 0; k < std::min(nb - 1, pl->n_streams); ++k) {  // join the side streams
+  for (int k = 0; k < std::min(side, pl->n_streams); ++k) {  // join the side streams
     LFR_CUDA(cudaEventRecord(pl->ev_join[k], pl->streams[k]));
     LFR_CUDA(cudaStreamWaitEvent(s, pl->ev_join[k], 0));
   }
@@ -414,7 +544,7 @@ int download(lfr_plan* pl, cudaStream_t s, double* positions, lfr_stats* st) {
     st->total_iterations = ti;
     st->total_line_search_steps = tl;
     st->n_solved = pl->n_solved;
-    st->n_kernel_launches = (uint32_t)pl->buckets.size();
+    st->n_kernel_launches = (uint32_t)pl->buckets.size() + (pl->n_large ? 1u : 0u);
   }
   return LFR_OK;
 }
@@ -507,7 +637,7 @@ int lfr_plan_solve(lfr_plan* pl, void* stream) {
 
 int lfr_plan_num_launches(const lfr_plan* pl) {
   // kernels only: the device-to-device reset of `positions` is a copy, not a kernel
-  return pl ? (int)pl->buckets.size() : 0;
+  return pl ? (int)pl->buckets.size() + (pl->n_large ? 1 : 0) : 0;
 }
 
 int lfr_plan_download(lfr_plan* pl, void* stream, double* positions, lfr_stats* st) {

@@ -54,6 +54,9 @@ CONFIGS = {
                         vis_halfwidth=8, seed=1004),
     "cfg5": SynthConfig("cfg5", 1000, 2000, "ring", 0.7, match_prob=0.3, window=20,
                         n_random=5, vis_halfwidth=12, seed=1005),
+    # a small ring scene whose components exceed 96 unknowns (exercises the CTA / PCG tier cheaply)
+    "ring60": SynthConfig("ring60", 60, 400, "ring", 0.7, match_prob=0.5, window=8,
+                          n_random=2, vis_halfwidth=10, seed=1060),
 }
 
 ALIASES = {"fountain": "cfg2", "herzjesu": "cfg3", "courtyard": "cfg4", "madrid": "cfg5", "tiny": "cfg1"}

@@ -108,6 +108,36 @@ def test_duplicate_pairs_take_the_serial_assembly_path(b200, oracle):
     _compare(b200, oracle, p)
 
 
+def test_cta_pcg_tier_on_large_components(b200, oracle):
+    """Components with more than 96 unknowns (ring scene, up to 60 nodes) take the
+    CTA tier: matrix-free block-Jacobi PCG to 1e-13 stands in for the exact solve."""
+    _, p = get_problem("ring60")
+    sizes = np.diff(p.comp_ptr.astype(np.int64))
+    assert (sizes > 49).sum() > 50
+    pos_g, st_g = b200.solve(p)
+    pos_o, st_o = oracle.solve(p, oracle.default_options(n_threads=8))
+    assert np.abs(pos_g - pos_o).max() <= TOL_UNITS
+    big = sizes > 49
+    # the linear solves agree to ~1e-12, so the trajectories coincide
+    assert np.array_equal(st_g["iterations"][big], st_o["iterations"][big])
+    assert np.array_equal(st_g["termination"], st_o["termination"])
+
+
+def test_forced_pcg_matches_cholesky_path(b200, oracle):
+    """lfr_options.linear_solver = 2 sends every component through the PCG tier."""
+    _, p = get_problem("cfg1")
+    pos_g, st_g = b200.solve(p, b200.default_options(linear_solver=2))
+    pos_o, st_o = oracle.solve(p, oracle.default_options(n_threads=1))
+    assert np.abs(pos_g - pos_o).max() <= TOL_UNITS
+    assert np.array_equal(st_g["iterations"], st_o["iterations"])
+    from lfr_b200 import synth, build_problem
+    p2 = build_problem(synth.generate("cfg2", scale=0.1, seed=3))
+    pos_g, st_g = b200.solve(p2, b200.default_options(linear_solver=2))
+    pos_o, st_o = oracle.solve(p2, oracle.default_options(n_threads=8))
+    assert np.abs(pos_g - pos_o).max() <= TOL_UNITS
+    assert np.array_equal(st_g["iterations"], st_o["iterations"])
+
+
 def test_plan_resolve_is_deterministic(b200):
     """Row-owned sums, no atomics: re-running the plan is bit-identical."""
     from lfr_b200.capi import Plan
