@@ -203,9 +203,10 @@ int upload(DevBuf* d, const T* h, size_t count, cudaStream_t s) {
 int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   static const int kClass[] = {2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 57344, kMaxSmemPerBlock};
   const int n_class = sizeof(kClass) / sizeof(kClass[0]);
-  static const int kVariant[3] = {16, 32, 0};
-  std::vector<std::vector<uint32_t>> members(3 * n_class);
-  std::vector<Bucket> caps(3 * n_class);
+  static const int kVariant[5] = {8, 16, 24, 32, 0};
+  const int kNV = 5;
+  std::vector<std::vector<uint32_t>> members(kNV * n_class);
+  std::vector<Bucket> caps(kNV * n_class);
   pl->comp_size.resize(p->n_components);
   pl->n_solved = 0;
   pl->buckets.clear();
@@ -236,9 +237,9 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       continue;
     }
     const int e = std::max<int>(1, (int)eup);
-    int vi = (n2 <= 16) ? 0 : (n2 <= 32 ? 1 : 2);
-    if (force_v1) vi = 2;
-    const int need = (vi == 2) ? lfr::WarpLayout(e, (int)nc, n2).total : lfr::Warp2Layout(e, (int)nc, n2).total;
+    int vi = (n2 <= 8) ? 0 : (n2 <= 16 ? 1 : (n2 <= 24 ? 2 : (n2 <= 32 ? 3 : 4)));
+    if (force_v1) vi = 4;
+    const int need = (vi == 4) ? lfr::WarpLayout(e, (int)nc, n2).total : lfr::Warp2Layout(e, (int)nc, n2).total;
     int k = 0;
     while (k < n_class && need > kClass[k]) ++k;
     if (k == n_class) return fail(LFR_EUNSUPPORTED, "component needs more shared memory than one SM has");
@@ -249,18 +250,18 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
     cb.n2max = std::max(cb.n2max, n2);
   }
   for (int k = n_class - 1; k >= 0; --k) {  // largest first
-    for (int vi = 2; vi >= 0; --vi) {
+    for (int vi = kNV - 1; vi >= 0; --vi) {
       const std::vector<uint32_t>& mem = members[vi * n_class + k];
       if (mem.empty()) continue;
       Bucket b = caps[vi * n_class + k];
       b.variant = kVariant[vi];
       b.n = (uint32_t)mem.size();
       b.offset = (uint32_t)pl->list_host.size();
-      b.smem_per_warp = (vi == 2) ? lfr::WarpLayout(b.emax, b.ncmax, b.n2max).total
+      b.smem_per_warp = (vi == 4) ? lfr::WarpLayout(b.emax, b.ncmax, b.n2max).total
                                   : lfr::Warp2Layout(b.emax, b.ncmax, b.n2max).total;
       if (b.smem_per_warp > kMaxSmemPerBlock) return fail(LFR_EUNSUPPORTED, "bucket exceeds shared memory");
       b.warps = (4 * b.smem_per_warp <= kMaxSmemPerBlock) ? 4 : 1;
-      if (b.warps == 1 && b.variant == 16) b.variant = 32;  // only <1,32> is instantiated for single-warp CTAs
+      if (b.warps == 1 && b.variant != 0) b.variant = 32;  // only <1,32> is instantiated for single-warp CTAs
       pl->list_host.insert(pl->list_host.end(), mem.begin(), mem.end());
       pl->buckets.push_back(b);
     }
@@ -433,7 +434,11 @@ int set_kernel_attrs() {
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp2_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp2_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp2_kernel<4, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp2_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
@@ -494,8 +499,12 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
     wb.smem_per_warp = b.smem_per_warp;
     const size_t smem = (size_t)b.smem_per_warp * b.warps;
     const unsigned grid = (b.n + b.warps - 1) / b.warps;
-    if (b.variant == 16)
+    if (b.variant == 8)
+      lfr::solve_warp2_kernel<4, 8><<<grid, 128, smem, bs>>>(P, pl->K, wb);
+    else if (b.variant == 16)
       lfr::solve_warp2_kernel<4, 16><<<grid, 128, smem, bs>>>(P, pl->K, wb);
+    else if (b.variant == 24 && b.warps == 4)
+      lfr::solve_warp2_kernel<4, 24><<<grid, 128, smem, bs>>>(P, pl->K, wb);
     else if (b.variant == 32 && b.warps == 4)
       lfr::solve_warp2_kernel<4, 32><<<grid, 128, smem, bs>>>(P, pl->K, wb);
     else if (b.variant == 32)

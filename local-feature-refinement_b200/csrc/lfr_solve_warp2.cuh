@@ -42,6 +42,7 @@ struct Warp2Layout {
     H = o; o += 8 * n2max * ldh;
     scr = o; o += 8 * 7 * emax;
     tup = o; o += 8 * 5 * emax;
+    o = align_up(o, 16);
     prow = o; o += 8 * 2 * 36;  // double-buffered pivot row of the elimination (32 columns, rhs, 1/pivot, pivot)
     eidx = o; o += 4 * emax;
     meta = o; o += 4 * emax;
@@ -271,32 +272,33 @@ __device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const
   // holds the current pivot column and ONE compact loop body serves every column
   // (a fully unrolled elimination is ~100 KB of straight-line code and stalls on
   // instruction fetch).
+  // No per-element guards: all NREG slots are processed every step (slots past
+  // the live columns hold zeros), so the step is a straight run of 128-bit
+  // shared-memory accesses and DFMAs that the scheduler can overlap freely.
   for (int j = 0; j < n; ++j) {
-    const int m = n - j;  // live columns j .. n-1 sit in slots 0 .. m-1
     double* buf = C.prow + (j & 1) * C.prow_stride;
+    double2* buf2 = reinterpret_cast<double2*>(buf);
     if (i == j) {
       const double piv = a[0];
       const double rp = 1.0 / piv;
-      buf[NREG + 1] = piv;
 #pragma unroll
-      for (int k = 1; k < NREG; ++k) {
-        if (k < m) {
-          a[k] *= rp;
-          buf[k] = a[k];
-        }
-      }
+      for (int k = 0; k < NREG; ++k) a[k] *= rp;
       b *= rp;
-      buf[NREG] = b;
+#pragma unroll
+      for (int k = 0; k < NREG; k += 2) buf2[k / 2] = make_double2(a[k], a[k + 1]);
+      buf2[NREG / 2] = make_double2(b, piv);
     }
     __syncwarp();
-    const double piv = buf[NREG + 1];
-    ok = ok && (piv > 0.0) && isfinite(piv);
+    double2 t[NREG / 2];
+#pragma unroll
+    for (int k = 0; k < NREG; k += 2) t[k / 2] = buf2[k / 2];
+    const double2 bp = buf2[NREG / 2];
+    ok = ok && (bp.y > 0.0) && isfinite(bp.y);
     const double f = (i == j) ? 0.0 : a[0];  // the pivot row itself is kept
 #pragma unroll
-    for (int k = 1; k < NREG; ++k) {
-      if (k < m) a[k - 1] = a[k] - f * buf[k];
-    }
-    b -= f * buf[NREG];
+    for (int k = 1; k < NREG; ++k) a[k - 1] = a[k] - f * ((k & 1) ? t[k / 2].y : t[k / 2].x);
+    a[NREG - 1] = 0.0;
+    b -= f * bp.x;
   }
   const double y = b;  // rows are normalised: the right-hand side is the solution
   double mc = 0.0, dot = 0.0, mx = 0.0;

@@ -43,6 +43,7 @@ class SynthConfig:
     n_random: int = 0     # ring: extra random partners per image
     vis_halfwidth: int = 0  # sequential / ring: a point is seen within this many frames of its centre
     seed: int = 0
+    outlier_match_ratio: float = 0.0  # > 0: cap a pair's outliers at this fraction of its inlier matches
 
 
 CONFIGS = {
@@ -52,8 +53,11 @@ CONFIGS = {
     "cfg3": SynthConfig("cfg3", 8, 8000, "exhaustive", 0.7, seed=1003),
     "cfg4": SynthConfig("cfg4", 38, 4000, "sequential", 0.7, window=10, loop=19,
                         vis_halfwidth=8, seed=1004),
+    # retrieval pairs share few points, so "5 % of K" outliers would be a third of all
+    # matches and glue hundreds of tracks together; cap them at 1/8 of the pair's inliers
+    # (the ratio the exhaustive configs have)
     "cfg5": SynthConfig("cfg5", 1000, 2000, "ring", 0.7, match_prob=0.3, window=20,
-                        n_random=5, vis_halfwidth=12, seed=1005),
+                        n_random=5, vis_halfwidth=12, seed=1005, outlier_match_ratio=0.125),
     # a small ring scene whose components exceed 96 unknowns (exercises the CTA / PCG tier cheaply)
     "ring60": SynthConfig("ring60", 60, 400, "ring", 0.7, match_prob=0.5, window=8,
                           n_random=2, vis_halfwidth=10, seed=1060),
@@ -140,6 +144,8 @@ def generate(cfg, scale: float = 1.0, seed: int | None = None) -> MatchSet:
         free_a = np.setdiff1d(np.arange(obs[a].shape[0]), ia, assume_unique=False)
         free_b = np.setdiff1d(np.arange(obs[b].shape[0]), ib, assume_unique=False)
         k = min(n_out, free_a.shape[0], free_b.shape[0])
+        if cfg.outlier_match_ratio > 0:
+            k = min(k, int(round(cfg.outlier_match_ratio * m)))
         if k > 0:
             oa = rng.choice(free_a, size=k, replace=False)
             ob = rng.choice(free_b, size=k, replace=False)
