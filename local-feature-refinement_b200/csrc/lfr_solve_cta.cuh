@@ -217,7 +217,8 @@ __device__ __forceinline__ void cta_matvec(const CtaCtx& C, const double* v, dou
 // Block-Jacobi PCG for (S H S + D^2) y = S g; dl = -S y.  Returns validity and
 // {model_cost_change, g . dl, |dl|_inf}.
 __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, const DevConsts& K, double* model_change,
-                                            double* gd, double* dmax, unsigned* cg_iters) {
+                                            double* gd, double* dmax, unsigned* cg_iters, bool diag_mode,
+                                            double* worst_res, unsigned* n_maxit) {
   // damping, preconditioner, initial residual
   double bb = 0.0, rz = 0.0, bad = 0.0;
   for (int f = C.tid; f < C.nf; f += kCtaThreads) {
@@ -289,6 +290,17 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
     }
   }
   *cg_iters += (unsigned)it;
+  if (diag_mode && ok && bb > 0.0) {  // LFR_PROFILE: true residual |b - A y| / |b| of the returned solution
+    if (it >= max_it) ++*n_maxit;
+    cta_matvec(C, C.y, C.w);
+    double e2 = 0.0, z1 = 0.0, z2 = 0.0;
+    for (int i = C.tid; i < C.n; i += kCtaThreads) {
+      const double d = C.S[i] * C.g[i] - C.w[i];
+      e2 += d * d;
+    }
+    block_sum3(C, e2, z1, z2);
+    *worst_res = fmax(*worst_res, sqrt(e2 / bb));
+  }
   double mc = 0.0, dot = 0.0, nonfinite = 0.0, mx = 0.0;
   for (int i = C.tid; i < C.n; i += kCtaThreads) {
     const double y = C.y[i], si = C.S[i], gi = C.g[i];
@@ -385,7 +397,8 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
   const double cost0 = cost;
   double radius = K.radius0, nu = 2.0;
   int iter = 0, n_invalid = 0, term = LFR_TERM_NO_CONVERGENCE;
-  unsigned ls_steps = 0, cg_iters = 0;
+  unsigned ls_steps = 0, cg_iters = 0, n_maxit = 0;
+  double worst_res = 0.0;
   bool success = true;
   auto norms = [&](double* xn2, double* dn2) {
     double a = 0.0, b = 0.0, z = 0.0;
@@ -417,7 +430,8 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
     ++iter;
     success = false;
     double model_change = 0.0, gd = 0.0, dmax = 0.0;
-    bool valid = cta_lm_step(C, radius, K, &model_change, &gd, &dmax, &cg_iters);
+    bool valid = cta_lm_step(C, radius, K, &model_change, &gd, &dmax, &cg_iters, P.st_cycles != nullptr, &worst_res,
+                             &n_maxit);
     valid = valid && (model_change > 0.0);
     if (!valid) {
       if (++n_invalid >= K.max_invalid) { term = LFR_TERM_FAILURE; break; }
@@ -504,8 +518,11 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
     P.st_ls[c] = ls_steps;
     if (P.st_cycles) {
       unsigned long long* o = P.st_cycles + 8 * (size_t)c;
-      o[0] = o[1] = o[2] = o[3] = o[5] = 0;
+      o[0] = o[1] = o[2] = 0;
+      o[3] = n_maxit;
+      o[5] = (unsigned long long)__double_as_longlong(worst_res);
       o[4] = cg_iters;
+      o[1] = 1;  // marks a CTA-tier component
       o[6] = (unsigned long long)ls_steps << 32;
       o[7] = 0;
     }

@@ -61,6 +61,8 @@ CONFIGS = {
     # a small ring scene whose components exceed 96 unknowns (exercises the CTA / PCG tier cheaply)
     "ring60": SynthConfig("ring60", 60, 400, "ring", 0.7, match_prob=0.5, window=8,
                           n_random=2, vis_halfwidth=10, seed=1060),
+    "ring200": SynthConfig("ring200", 200, 150, "ring", 0.7, match_prob=0.4, window=12,
+                           n_random=3, vis_halfwidth=10, seed=1200, outlier_match_ratio=0.125),
 }
 
 ALIASES = {"fountain": "cfg2", "herzjesu": "cfg3", "courtyard": "cfg4", "madrid": "cfg5", "tiny": "cfg1"}
