@@ -90,7 +90,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "250"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -241,6 +241,7 @@ def run_b200(args):
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_per_step = float(np.mean(step_ms))
+    ms_per_step_median = float(np.median(step_ms))
     _, st = plan.download(stream)
     alg_bytes, one_pass = plan.traffic(stream)
     launches = plan.num_launches()
@@ -263,6 +264,8 @@ def run_b200(args):
             e2e_t.append(dt)
             e2e_parts.append((stt.h2d_ms, stt.kernel_ms, stt.d2h_ms))
     e2e_ms = 1e3 * float(np.mean(e2e_t))
+    if os.environ.get("LFR_BENCH_DEBUG"):
+        sys.stderr.write("e2e steps ms: %s\nparts: %s\n" % ([round(1e3 * x, 3) for x in e2e_t], [[round(y, 3) for y in x] for x in e2e_parts]))
     e2e_break = [float(x) for x in np.mean(np.array(e2e_parts), axis=0)]
     clocks = sampler.stop() if sampler else None
     # ---- reduce over ranks --------------------------------------------------------------------
@@ -304,7 +307,9 @@ def run_b200(args):
             "l2": "flushed between timed steps (256 MiB write, untimed)",
             "lm_iterations_per_step": int(st["total_iterations"])}),
         "lm_iters_per_s": tot_iters / (ms_per_step / 1e3),
+        "ms_per_step_median": ms_per_step_median,
         "e2e": {"value": tot_tracks / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "ms_per_step_median": 1e3 * float(np.median(e2e_t)),
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": "lfr_solve() (include/lfr.h) with pinned host buffers",
                 "stages_ms": {"h2d_and_schedule": e2e_break[0], "kernels": e2e_break[1], "d2h": e2e_break[2]}},
