@@ -171,7 +171,7 @@ __device__ __forceinline__ double bracket_root(const double* q, int nq, double a
       x -= dx;
       if (t == x) return x;
     }
-    if (fabs(dx) <= 4e-16 * fabs(x)) return x;
+    if (fabs(dx) <= 1e-13 * fabs(x)) return x;  // Newton converges quadratically: the next step would be ~1e-26
     horner2(q, nq, x, &f, &df);
     if (f < 0.0) xl = x; else xh = x;
   }
@@ -262,6 +262,7 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
                                                  bool three, double x2, double f2, double g2, double lo,
                                                  double hi, int lane) {
   const double h = three ? fmax(x1, x2) : x1;
+  const double ih = 1.0 / h;  // the only division by h: t = x * ih
   const double g0h = g0 * h;
   double c[6];
   int nc;
@@ -274,7 +275,7 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
     nc = 4;
   } else {
     double A[4][5];
-    const double ts[2] = {x1 / h, x2 / h};
+    const double ts[2] = {x1 * ih, x2 * ih};
     const double fs[2] = {f1, f2}, gs[2] = {g1, g2};
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -285,6 +286,7 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
       A[2 * q + 1][4] = (gs[q] - g0) * h;
     }
     // Gaussian elimination with partial pivoting, fully unrolled (registers)
+    double ipiv[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -298,9 +300,10 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
           }
         }
       }
+      ipiv[k] = 1.0 / A[k][k];  // one reciprocal per pivot
 #pragma unroll
       for (int i = k + 1; i < 4; ++i) {
-        const double mlt = A[i][k] / A[k][k];
+        const double mlt = A[i][k] * ipiv[k];
 #pragma unroll
         for (int j = k; j < 5; ++j) A[i][j] -= mlt * A[k][j];
       }
@@ -311,17 +314,17 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
       double acc = A[i][4];
 #pragma unroll
       for (int j = i + 1; j < 4; ++j) acc -= A[i][j] * d[j];
-      d[i] = acc / A[i][i];
+      d[i] = acc * ipiv[i];
     }
     c[0] = d[3]; c[1] = d[2]; c[2] = d[1]; c[3] = d[0];
     c[4] = g0h;
     c[5] = f0;
     nc = 6;
   }
-  const double tlo = lo / h, thi = hi / h;
+  const double tlo = lo * ih, thi = hi * ih;
   // MinimizePolynomial: middle, ends, real parts of the roots of p'
   double ox = (lo + hi) / 2.0;
-  double ov = poly_eval(c, nc, ox / h);
+  double ov = poly_eval(c, nc, ox * ih);
   double v = poly_eval(c, nc, tlo);
   if (v < ov) { ov = v; ox = lo; }
   v = poly_eval(c, nc, thi);
@@ -339,7 +342,7 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
   const double sx[3] = {0.0, x1, x2};
   for (int i = 0; i < (three ? 3 : 2); ++i) {
     if (sx[i] < lo || sx[i] > hi) continue;
-    v = poly_eval(c, nc, sx[i] / h);
+    v = poly_eval(c, nc, sx[i] * ih);
     if (v < ov) { ov = v; ox = sx[i]; }
   }
   return ox;

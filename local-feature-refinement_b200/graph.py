@@ -385,9 +385,102 @@ class Problem:
         return int(self.comp_ptr.shape[0] - 1)
 
 
-def build_problem(ms: MatchSet, banned_images=(), log=None) -> Problem:
-    """solve.cc:405-606 end to end."""
+def build_problem_native(ms: MatchSet, banned_images=(), log=None) -> Problem:
+    """solve.cc:405-606 through the native host stage (csrc/lfr_host.cc, include/lfr_host.h)."""
+    import ctypes as C
+    from .capi import load_b200
+
+    class HostInput(C.Structure):
+        _fields_ = [("n_pairs", C.c_uint64), ("n_matches", C.c_uint64), ("n_images", C.c_uint32),
+                    ("pair_img1", C.c_void_p), ("pair_img2", C.c_void_p), ("pair_skip", C.c_void_p),
+                    ("pair_ptr", C.c_void_p), ("feat1", C.c_void_p), ("feat2", C.c_void_p), ("sim", C.c_void_p),
+                    ("disp1", C.c_void_p), ("disp2", C.c_void_p)]
+
+    class HostSizes(C.Structure):
+        _fields_ = [("n_nodes", C.c_uint32), ("n_tracks", C.c_uint32), ("n_components", C.c_uint32),
+                    ("n_images_seen", C.c_uint32), ("max_track_size", C.c_uint32), ("max_component_size", C.c_uint32),
+                    ("n_meta_components", C.c_uint32), ("n_oversized_meta_components", C.c_uint32),
+                    ("n_cut_groups", C.c_uint32), ("reserved", C.c_uint32), ("n_edges", C.c_uint64),
+                    ("tracks_ms", C.c_double), ("graph_cut_ms", C.c_double)]
+
+    L = load_b200().lib
+    L.lfr_host_stage_create.argtypes = [C.POINTER(HostInput), C.POINTER(C.c_void_p), C.POINTER(HostSizes)]
+    L.lfr_host_stage_create.restype = C.c_int
+    L.lfr_host_stage_export.argtypes = [C.c_void_p] * 11
+    L.lfr_host_stage_export.restype = C.c_int
+    L.lfr_host_stage_destroy.argtypes = [C.c_void_p]
+    L.lfr_host_stage_destroy.restype = None
+    say = log if log is not None else (lambda s: None)
+    banned = set(banned_images)
+    skip = np.array([(ms.image_names[a] in banned) or (ms.image_names[b] in banned)
+                     for a, b in zip(ms.pair_img1.tolist(), ms.pair_img2.tolist())], dtype=np.uint8) \
+        if banned else np.zeros(ms.n_pairs, dtype=np.uint8)
+    arrs = dict(
+        pair_img1=np.ascontiguousarray(ms.pair_img1, dtype=np.uint32), pair_img2=np.ascontiguousarray(ms.pair_img2, dtype=np.uint32),
+        pair_skip=skip, pair_ptr=np.ascontiguousarray(ms.pair_ptr, dtype=np.uint64),
+        feat1=np.ascontiguousarray(ms.feat1, dtype=np.uint32), feat2=np.ascontiguousarray(ms.feat2, dtype=np.uint32),
+        sim=np.ascontiguousarray(ms.sim, dtype=np.float32), disp1=np.ascontiguousarray(ms.disp1, dtype=np.float32),
+        disp2=np.ascontiguousarray(ms.disp2, dtype=np.float32))
+    inp = HostInput(n_pairs=ms.n_pairs, n_matches=ms.n_matches, n_images=len(ms.image_names),
+                    **{k: (v.ctypes.data if v.size else None) for k, v in arrs.items()})
+    h = C.c_void_p()
+    sz = HostSizes()
+    rc = L.lfr_host_stage_create(C.byref(inp), C.byref(h), C.byref(sz))
+    if rc != 0:
+        raise RuntimeError("lfr_host_stage_create failed (%d)" % rc)
+    try:
+        N, E, Cn = int(sz.n_nodes), int(sz.n_edges), int(sz.n_components)
+        row_ptr = np.zeros(N + 1, np.uint32); edges = np.zeros(E, EDGE_DTYPE)
+        track = np.zeros(N, np.uint32); comp = np.zeros(N, np.uint32); is_root = np.zeros(N, np.uint8)
+        comp_ptr = np.zeros(Cn + 1, np.uint32); comp_nodes = np.zeros(N, np.uint32); comp_order = np.zeros(Cn, np.uint32)
+        node_image = np.zeros(N, np.uint32); node_feat = np.zeros(N, np.uint32)
+        outs = [row_ptr, edges, track, comp, is_root, comp_ptr, comp_nodes, comp_order, node_image, node_feat]
+        rc = L.lfr_host_stage_export(h, *[(a.ctypes.data if a.size else None) for a in outs])
+        if rc != 0:
+            raise RuntimeError("lfr_host_stage_export failed (%d)" % rc)
+    finally:
+        L.lfr_host_stage_destroy(h)
+    image_fact: Dict[int, float] = {}
+    for a, b, fa, fb, sk in zip(ms.pair_img1.tolist(), ms.pair_img2.tolist(), ms.pair_fact1.tolist(),
+                                ms.pair_fact2.tolist(), skip.tolist()):
+        if sk:
+            continue
+        image_fact.setdefault(a, fa)
+        image_fact.setdefault(b, fb)
+    g = MatchGraph(n_nodes=N, node_image=node_image.astype(np.int64), node_feat=node_feat,
+                   und_sim=np.zeros(0), und_n1=np.zeros(0, np.int64), und_n2=np.zeros(0, np.int64),
+                   row_ptr=row_ptr, edges=edges, image_names=ms.image_names, image_fact=image_fact,
+                   n_images=int(sz.n_images_seen))
+    say("# graph nodes: %d" % N)
+    say("# graph edges: %d" % E)
+    info: dict = {}
+    if N == 0:
+        z32 = np.zeros(0, dtype=np.uint32)
+        return Problem(g, z32, z32, np.zeros(0, np.uint8), np.zeros(1, np.uint32), z32, z32, info)
+    say("# tracks: %d" % sz.n_tracks)
+    say("max track size: %d" % sz.max_track_size)
+    say("Graph-cut time: %dms" % int(sz.graph_cut_ms))
+    say("# components: %d" % Cn)
+    say("max component size: %d" % sz.max_component_size)
+    info.update(n_tracks=int(sz.n_tracks), n_components=Cn, max_component_size=int(sz.max_component_size),
+                tracks_ms=float(sz.tracks_ms), graph_cut_ms=float(sz.graph_cut_ms),
+                n_meta_components=int(sz.n_meta_components),
+                n_oversized_meta_components=int(sz.n_oversized_meta_components), n_cut_groups=int(sz.n_cut_groups),
+                host_stage="native")
+    return Problem(graph=g, track=track, comp=comp, is_root=is_root, comp_ptr=comp_ptr, comp_nodes=comp_nodes,
+                   comp_order=comp_order.astype(np.int64), info=info)
+
+
+def build_problem(ms: MatchSet, banned_images=(), log=None, native: Optional[bool] = None) -> Problem:
+    """solve.cc:405-606 end to end.  Uses the native host stage (csrc/lfr_host.cc)
+    unless native=False or LFR_HOST_PYTHON=1 selects the numpy implementation below
+    (the two are tested to agree exactly)."""
+    import os
     import time
+    if native is None:
+        native = not os.environ.get("LFR_HOST_PYTHON")
+    if native:
+        return build_problem_native(ms, banned_images, log)
     g = build_graph(ms, banned_images)
     say = log if log is not None else (lambda s: None)
     say("# graph nodes: %d" % g.n_nodes)                       # solve.cc:484
@@ -419,7 +512,7 @@ def build_problem(ms: MatchSet, banned_images=(), log=None) -> Problem:
     comp_ptr = np.zeros(n_comp + 1, dtype=np.uint32)
     np.cumsum(sizes[comp_order], out=comp_ptr[1:])
     info.update(n_tracks=n_tracks, n_components=n_comp, max_component_size=int(sizes[comp_order[0]]),
-                tracks_ms=(t1 - t0) * 1e3, graph_cut_ms=(t2 - t1) * 1e3)
+                tracks_ms=(t1 - t0) * 1e3, graph_cut_ms=(t2 - t1) * 1e3, host_stage="numpy")
     return Problem(
         graph=g, track=track.astype(np.uint32), comp=comp.astype(np.uint32), is_root=is_root,
         comp_ptr=comp_ptr, comp_nodes=comp_nodes, comp_order=comp_order.astype(np.int64), info=info,

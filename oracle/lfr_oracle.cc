@@ -195,7 +195,7 @@ double bracket_root(const double* q, int nq, double a, double b, double fa, doub
       x -= dx;
       if (t == x) return x;
     }
-    if (std::fabs(dx) <= 4e-16 * std::fabs(x)) return x;
+    if (std::fabs(dx) <= 1e-13 * std::fabs(x)) return x;  // Newton converges quadratically: the next step would be ~1e-26
     horner2(q, nq, x, &f, &df);
     if (f < 0.0) xl = x; else xh = x;
   }
@@ -276,6 +276,7 @@ int real_roots_in(const double* c, int n, double lo, double hi, double* out) {
 double hermite_minimizer(double f0, double g0, double x1, double f1, double g1, bool three, double x2,
                          double f2, double g2, double lo, double hi, double* value) {
   const double h = three ? std::max(x1, x2) : x1;
+  const double ih = 1.0 / h;  // the only division by h: t = x * ih
   const double g0h = g0 * h;
   double c[6];
   int nc;
@@ -288,7 +289,7 @@ double hermite_minimizer(double f0, double g0, double x1, double f1, double g1, 
     nc = 4;
   } else {
     double A[4][5];
-    const double ts[2] = {x1 / h, x2 / h};
+    const double ts[2] = {x1 * ih, x2 * ih};
     const double fs[2] = {f1, f2}, gs[2] = {g1, g2};
     for (int q = 0; q < 2; ++q) {
       const double t = ts[q], t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
@@ -298,12 +299,14 @@ double hermite_minimizer(double f0, double g0, double x1, double f1, double g1, 
       A[2 * q + 1][3] = 5.0 * t4;
       A[2 * q + 1][4] = (gs[q] - g0) * h;
     }
+    double ipiv[4];
     for (int k = 0; k < 4; ++k) {
       for (int i = k + 1; i < 4; ++i)
         if (std::fabs(A[i][k]) > std::fabs(A[k][k]))
           for (int j = 0; j < 5; ++j) std::swap(A[k][j], A[i][j]);
+      ipiv[k] = 1.0 / A[k][k];  // one reciprocal per pivot
       for (int i = k + 1; i < 4; ++i) {
-        const double mlt = A[i][k] / A[k][k];
+        const double mlt = A[i][k] * ipiv[k];
         for (int j = k; j < 5; ++j) A[i][j] -= mlt * A[k][j];
       }
     }
@@ -311,16 +314,16 @@ double hermite_minimizer(double f0, double g0, double x1, double f1, double g1, 
     for (int i = 3; i >= 0; --i) {
       double acc = A[i][4];
       for (int j = i + 1; j < 4; ++j) acc -= A[i][j] * d[j];
-      d[i] = acc / A[i][i];
+      d[i] = acc * ipiv[i];
     }
     c[0] = d[3]; c[1] = d[2]; c[2] = d[1]; c[3] = d[0];
     c[4] = g0h;
     c[5] = f0;
     nc = 6;
   }
-  const double tlo = lo / h, thi = hi / h;
+  const double tlo = lo * ih, thi = hi * ih;
   double ox = (lo + hi) / 2.0;  // MinimizePolynomial starts from the middle
-  double ov = poly_eval(c, nc, ox / h);
+  double ov = poly_eval(c, nc, ox * ih);
   double v = poly_eval(c, nc, tlo);
   if (v < ov) { ov = v; ox = lo; }
   v = poly_eval(c, nc, thi);
@@ -337,7 +340,7 @@ double hermite_minimizer(double f0, double g0, double x1, double f1, double g1, 
   const double sx[3] = {0.0, x1, x2};
   for (int i = 0; i < (three ? 3 : 2); ++i) {
     if (sx[i] < lo || sx[i] > hi) continue;
-    v = poly_eval(c, nc, sx[i] / h);
+    v = poly_eval(c, nc, sx[i] * ih);
     if (v < ov) { ov = v; ox = sx[i]; }
   }
   if (value) *value = ov;

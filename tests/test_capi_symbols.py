@@ -17,14 +17,15 @@ def declared(header):
 
 
 def test_every_declared_symbol_is_exported(b200):
-    names = declared("lfr.h") + declared("lfr_wire.h")
-    assert "lfr_solve" in names and "lfr_wire_decode_matches" in names and len(names) >= 16
+    names = sorted(set(declared("lfr.h") + declared("lfr_wire.h") + declared("lfr_host.h")))
+    assert "lfr_solve" in names and "lfr_wire_decode_matches" in names and "lfr_host_stage_create" in names
     for n in names:
         assert hasattr(b200.lib, n), n
     assert b200.backend == "b200"
     from lfr_b200.capi import ABI_SYMBOLS
     from lfr_b200.wire import WIRE_SYMBOLS
-    assert sorted(ABI_SYMBOLS + WIRE_SYMBOLS) == names
+    host = ["lfr_host_stage_create", "lfr_host_stage_export", "lfr_host_stage_destroy"]
+    assert sorted(ABI_SYMBOLS + WIRE_SYMBOLS + host) == names
 
 
 def test_oracle_exports_the_same_abi(oracle):

@@ -33,7 +33,7 @@ def test_stage_matches_literal_restatement(cfg, scale, seed):
     # similarity ties exercise the (sim, n1, n2) tie-breaks
     ms.sim[:] = np.round(ms.sim * 20) / 20
     nodes, edges, images = ref.build_graph(as_pairs(ms))
-    g = build_graph(ms)
+    g = build_graph(ms)                      # the numpy stage, function by function
     assert g.n_nodes == len(nodes) and g.n_images == len(images)
     assert [ms.image_names[i] for i in g.node_image.tolist()] == [n["image_name"] for n in nodes]
     assert g.node_feat.tolist() == [n["feature_idx"] for n in nodes]
@@ -74,6 +74,29 @@ def test_partition_invariants(cfg, scale):
     assert [c for c, _ in d_ref] == p.comp_order.tolist()
     for slot, (c, nodes_c) in enumerate(d_ref[:200]):
         assert p.comp_nodes[p.comp_ptr[slot]:p.comp_ptr[slot + 1]].tolist() == nodes_c
+
+
+@pytest.mark.parametrize("cfg,scale,seed", [("cfg1", 1.0, None), ("cfg2", 0.1, 4), ("cfg4", 0.1, 8), ("ring60", 0.5, 2),
+                                            ("cfg2", 1.0, None)])
+def test_native_host_stage_equals_numpy_stage(cfg, scale, seed):
+    """csrc/lfr_host.cc (include/lfr_host.h) against graph.py, array for array."""
+    ms = synth.generate(cfg, scale=scale, seed=seed)
+    ms.sim[:] = np.round(ms.sim * 50) / 50          # similarity ties
+    a = build_problem(ms, native=True)
+    b = build_problem(ms, native=False)
+    assert a.info["host_stage"] == "native" and b.info["host_stage"] == "numpy"
+    for k in ("track", "comp", "is_root", "comp_ptr", "comp_nodes", "comp_order"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(a.graph.row_ptr, b.graph.row_ptr) and a.graph.edges.tobytes() == b.graph.edges.tobytes()
+    assert np.array_equal(a.graph.node_image, b.graph.node_image) and np.array_equal(a.graph.node_feat, b.graph.node_feat)
+    assert a.graph.n_images == b.graph.n_images and a.graph.image_fact == b.graph.image_fact
+    for k in ("n_tracks", "n_components", "max_component_size", "n_meta_components", "n_oversized_meta_components",
+              "n_cut_groups"):
+        assert a.info[k] == b.info[k], k
+    pb = build_problem(ms, banned_images=[ms.image_names[1]], native=True)
+    qb = build_problem(ms, banned_images=[ms.image_names[1]], native=False)
+    assert np.array_equal(pb.comp, qb.comp) and np.array_equal(pb.comp_nodes, qb.comp_nodes)
+    assert pb.graph.n_images == qb.graph.n_images and pb.graph.image_fact == qb.graph.image_fact
 
 
 def test_banned_images_and_empty_input():
