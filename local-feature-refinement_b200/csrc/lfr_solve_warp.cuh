@@ -240,16 +240,31 @@ __device__ __forceinline__ bool lm_step(const WarpCtx& C, double radius, const D
   bool ok = true;
   for (int j = 0; j < n; ++j) {
     const double* Aj = C.A + tri(j);
+    // rows j + lane + 32 p of this column, all passes in ONE k-loop: four
+    // independent accumulators share the broadcast load of A[j][k]
     double s[4];
+    const double* Ar[4];
+    const int npass = (n - j) / 32 + 1;  // passes that have at least one live row (warp-uniform)
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int i = j + C.lane + 32 * p;
-      s[p] = 0.0;
-      if (i <= n) {
-        const double* Ai = C.A + tri(i);
-        double acc = Ai[j];
-        for (int k = 0; k < j; ++k) acc -= Ai[k] * Aj[k];
-        s[p] = acc;
+      const bool live = i <= n;
+      Ar[p] = C.A + tri(live ? i : j);  // dead lanes shadow row j (harmless, never stored)
+      s[p] = Ar[p][j];
+    }
+    if (npass == 1) {
+      for (int k = 0; k < j; ++k) s[0] -= Ar[0][k] * Aj[k];
+    } else if (npass == 2) {
+      for (int k = 0; k < j; ++k) {
+        const double ajk = Aj[k];
+        s[0] -= Ar[0][k] * ajk;
+        s[1] -= Ar[1][k] * ajk;
+      }
+    } else {
+      for (int k = 0; k < j; ++k) {
+        const double ajk = Aj[k];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) s[p] -= Ar[p][k] * ajk;
       }
     }
     const double sjj = __shfl_sync(kFull, s[0], 0);
