@@ -164,6 +164,52 @@ def test_forced_pcg_matches_cholesky_path(b200, oracle):
     assert np.array_equal(st_g["iterations"], st_o["iterations"])
 
 
+def test_edge_cases_empty_zero_and_singletons(b200, oracle):
+    """Empty graph, SKIP_REFINEMENT-style all-zero grids (compute_match_graph.py:150-152),
+    a graph whose components are all single nodes, and roots-only components."""
+    from lfr_b200 import MatchSet, build_problem, synth
+    ms = synth.generate("cfg1")
+    empty = build_problem(ms, banned_images=ms.image_names)
+    pos, st = b200.solve(empty)
+    assert pos.shape == (0, 2) and st["n_solved"] == 0
+    zero = synth.generate("cfg1")
+    zero.disp1[:] = 0
+    zero.disp2[:] = 0
+    p = build_problem(zero)
+    pos, st = b200.solve(p)
+    pos_o, st_o = oracle.solve(p)
+    assert np.all(pos == 0) and np.array_equal(st["iterations"], st_o["iterations"])
+    assert np.array_equal(st["termination"], st_o["termination"])
+    # every component a singleton: nothing is solved, positions (even non-zero starts) are untouched
+    q = build_problem(ms)
+    import copy
+    single = copy.copy(q)
+    n = q.graph.n_nodes
+    single.comp = np.arange(n, dtype=np.uint32)
+    single.comp_ptr = np.arange(n + 1, dtype=np.uint32)
+    single.comp_nodes = np.arange(n, dtype=np.uint32)
+    single.comp_order = np.arange(n)
+    init = np.random.default_rng(0).uniform(-2, 2, size=(n, 2))
+    pos, st = b200.solve(single, positions=init)
+    assert np.array_equal(pos, init) and st["n_solved"] == 0 and np.all(st["termination"] == 0)
+
+
+def test_malformed_edges_are_reported(b200):
+    """dst out of range / self edges are caught while the edges are staged on the device."""
+    import copy
+    _, p = get_problem("cfg1")
+    bad = copy.copy(p)
+    bad.graph = copy.copy(p.graph)
+    e = p.graph.edges.copy()
+    e["dst"][5] = p.graph.n_nodes + 7
+    bad.graph.edges = e
+    with pytest.raises(RuntimeError, match=r"\(-1\)"):
+        b200.solve(bad)
+    # the library stays usable afterwards
+    pos, st = b200.solve(p)
+    assert st["n_solved"] > 0
+
+
 def test_plan_resolve_is_deterministic(b200):
     """Row-owned sums, no atomics: re-running the plan is bit-identical."""
     from lfr_b200.capi import Plan
