@@ -275,32 +275,31 @@ __device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const
   // No per-element guards: all NREG slots are processed every step (slots past
   // the live columns hold zeros), so the step is a straight run of 128-bit
   // shared-memory accesses and DFMAs that the scheduler can overlap freely.
+  double myrp = 1.0;
   for (int j = 0; j < n; ++j) {
     double* buf = C.prow + (j & 1) * C.prow_stride;
     double2* buf2 = reinterpret_cast<double2*>(buf);
-    if (i == j) {
-      const double piv = a[0];
-      const double rp = 1.0 / piv;
-#pragma unroll
-      for (int k = 0; k < NREG; ++k) a[k] *= rp;
-      b *= rp;
+    if (i == j) {  // the pivot lane only publishes its registers (slot 0 = the pivot)
 #pragma unroll
       for (int k = 0; k < NREG; k += 2) buf2[k / 2] = make_double2(a[k], a[k + 1]);
-      buf2[NREG / 2] = make_double2(b, piv);
+      buf[NREG] = b;
     }
     __syncwarp();
     double2 t[NREG / 2];
 #pragma unroll
     for (int k = 0; k < NREG; k += 2) t[k / 2] = buf2[k / 2];
-    const double2 bp = buf2[NREG / 2];
-    ok = ok && (bp.y > 0.0) && isfinite(bp.y);
-    const double f = (i == j) ? 0.0 : a[0];  // the pivot row itself is kept
+    const double bj = buf[NREG];
+    const double piv = t[0].x;
+    ok = ok && (piv > 0.0) && isfinite(piv);
+    const double rp = 1.0 / piv;  // every lane: no serial work in the pivot lane
+    if (i == j) myrp = rp;
+    const double f = (i == j) ? 0.0 : a[0] * rp;  // the pivot row itself is kept (un-normalised)
 #pragma unroll
     for (int k = 1; k < NREG; ++k) a[k - 1] = a[k] - f * ((k & 1) ? t[k / 2].y : t[k / 2].x);
     a[NREG - 1] = 0.0;
-    b -= f * bp.x;
+    b -= f * bj;
   }
-  const double y = b;  // rows are normalised: the right-hand side is the solution
+  const double y = b * myrp;  // row i now reads  piv_i * y_i = b_i
   double mc = 0.0, dot = 0.0, mx = 0.0;
   bool finite = true;
   if (act) {
