@@ -177,6 +177,7 @@ __device__ __forceinline__ double cta_assemble(const CtaCtx& C, bool first, cons
 // w = (S H S + D^2) v, matrix-free.
 __device__ __forceinline__ void cta_matvec(const CtaCtx& C, const double* v, double* w) {
   const size_t E = C.Ec;
+#pragma unroll 4
   for (int j = C.tid; j < C.Ec; j += kCtaThreads) {
     const uint32_t mt = C.meta[j];
     const int fs = C.freeof[mt & 0x3fff], fd = C.freeof[(mt >> 14) & 0x3fff];
@@ -198,11 +199,13 @@ __device__ __forceinline__ void cta_matvec(const CtaCtx& C, const double* v, dou
   for (int f = C.tid; f < C.nf; f += kCtaThreads) {
     const int l = C.lof[f];
     double a0 = 0., a1 = 0.;
+#pragma unroll 4
     for (uint32_t j = C.outptr[l]; j < C.outptr[l + 1]; ++j) {
       const double q0 = C.q[2 * (size_t)j], q1 = C.q[2 * (size_t)j + 1];
       a0 -= C.scr[3 * E + j] * q0 + C.scr[5 * E + j] * q1;   // -M^T q
       a1 -= C.scr[4 * E + j] * q0 + C.scr[6 * E + j] * q1;
     }
+#pragma unroll 4
     for (uint32_t t = C.inptr[l]; t < C.inptr[l + 1]; ++t) {
       const uint32_t j = C.inlist[t];
       a0 += C.q[2 * (size_t)j];
