@@ -139,7 +139,7 @@ struct lfr_plan {
   // CTA tier (block-Jacobi PCG): components with more than kMaxWarpN2 unknowns, or all with linear_solver = 2
   std::vector<uint32_t> large_slots;
   uint32_t n_large = 0;
-  DevBuf L_comps, L_eidx, L_meta, L_inlist, L_scr, L_q, L_node, L_outptr, L_inptr, L_freeof, L_x, L_xc, L_lof, L_vec;
+  DevBuf L_comps, L_eidx, L_meta, L_inlist, L_twin, L_fdst, L_bmat, L_scr, L_q, L_node, L_outptr, L_inptr, L_freeof, L_x, L_xc, L_lof, L_vec;
   uint64_t L_total_free = 0;
   uint32_t n_solved = 0;
   bool profile = false;
@@ -178,7 +178,7 @@ void free_plan(lfr_plan* pl) {
   DevBuf* bufs[] = {&pl->row_ptr, &pl->edges, &pl->track, &pl->comp, &pl->is_root, &pl->comp_ptr, &pl->comp_nodes,
                     &pl->local_of, &pl->pos, &pl->pos_init, &pl->iter, &pl->term, &pl->cost0, &pl->cost1, &pl->ls,
                     &pl->kept, &pl->cycles, &pl->lists, &pl->err, &pl->L_comps, &pl->L_eidx, &pl->L_meta,
-                    &pl->L_inlist, &pl->L_scr, &pl->L_q, &pl->L_node, &pl->L_outptr, &pl->L_inptr, &pl->L_freeof,
+                    &pl->L_inlist, &pl->L_twin, &pl->L_fdst, &pl->L_bmat, &pl->L_scr, &pl->L_q, &pl->L_node, &pl->L_outptr, &pl->L_inptr, &pl->L_freeof,
                     &pl->L_x, &pl->L_xc, &pl->L_lof, &pl->L_vec};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < pl->n_streams; ++i) {
@@ -277,8 +277,8 @@ int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
   pl->L_total_free = 0;
   if (pl->n_large == 0) return LFR_OK;
   std::vector<lfr::CtaComp> comps(pl->n_large);
-  std::vector<uint32_t> eidx, meta, inlist, node, outptr, inptr, lof;
-  std::vector<int32_t> freeof;
+  std::vector<uint32_t> eidx, meta, inlist, twin, node, outptr, inptr, lof;
+  std::vector<int32_t> freeof, fdst;
   std::vector<int32_t> local(p->n_nodes, -1);
   uint64_t e_off = 0, n_off = 0, f_off = 0;
   for (uint32_t k = 0; k < pl->n_large; ++k) {
@@ -329,16 +329,33 @@ int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
       }
     }
     for (uint32_t l = 0; l < nc; ++l) local[p->comp_nodes[beg + l]] = -1;
+    // twin (reverse edge) of every kept edge and the destination's free index
+    bool regular = true;
+    twin.resize(e0 + ec);
+    fdst.resize(e0 + ec);
+    const size_t op0 = outptr.size() - (nc + 1), fo0 = freeof.size() - nc;
+    for (uint32_t j = 0; j < ec; ++j) {
+      const uint32_t sl = meta[e0 + j] & 0x3fff, dl = (meta[e0 + j] >> 14) & 0x3fff;
+      uint32_t found = 0, tw = j;
+      for (uint32_t t = outptr[op0 + dl]; t < outptr[op0 + dl + 1]; ++t)
+        if (((meta[e0 + t] >> 14) & 0x3fff) == sl) {
+          tw = t;
+          ++found;
+        }
+      if (found != 1) regular = false;
+      twin[e0 + j] = tw;
+      fdst[e0 + j] = freeof[fo0 + dl];
+    }
     lfr::CtaComp& cc = comps[k];
     cc.slot = c;
     cc.Nc = nc;
     cc.Ec = ec;
     cc.nf = nf;
+    cc.regular = regular ? 1u : 0u;
     cc.e_off = e_off;
     cc.n_off = n_off;
     cc.f_off = f_off;
     cc.comp_index = k;
-    cc.pad = 0;
     e_off += ec;
     n_off += nc;
     f_off += nf;
@@ -348,6 +365,9 @@ int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
   LFR_TRY(upload(&pl->L_eidx, eidx.data(), eidx.size(), s));
   LFR_TRY(upload(&pl->L_meta, meta.data(), meta.size(), s));
   LFR_TRY(upload(&pl->L_inlist, inlist.data(), inlist.size(), s));
+  LFR_TRY(upload(&pl->L_twin, twin.data(), twin.size(), s));
+  LFR_TRY(upload(&pl->L_fdst, fdst.data(), fdst.size(), s));
+  LFR_TRY(pl->L_bmat.reserve(sizeof(double) * 4 * std::max<uint64_t>(e_off, 1)));
   LFR_TRY(upload(&pl->L_node, node.data(), node.size(), s));
   LFR_TRY(upload(&pl->L_outptr, outptr.data(), outptr.size(), s));
   LFR_TRY(upload(&pl->L_inptr, inptr.data(), inptr.size(), s));
@@ -357,7 +377,7 @@ int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
   LFR_TRY(pl->L_q.reserve(sizeof(double) * 2 * std::max<uint64_t>(e_off, 1)));
   LFR_TRY(pl->L_x.reserve(sizeof(double) * 2 * std::max<uint64_t>(n_off, 1)));
   LFR_TRY(pl->L_xc.reserve(sizeof(double) * 2 * std::max<uint64_t>(n_off, 1)));
-  LFR_TRY(pl->L_vec.reserve(sizeof(double) * (2 * lfr::V_COUNT + 6) * std::max<uint64_t>(f_off, 1)));
+  LFR_TRY(pl->L_vec.reserve(sizeof(double) * (2 * lfr::V_COUNT + 9) * std::max<uint64_t>(f_off, 1)));
   // the upload sources above are locals: make sure the copies are done before they go away
   LFR_CUDA(cudaStreamSynchronize(s));
   return LFR_OK;
@@ -468,6 +488,9 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
     A.eidx = pl->L_eidx.as<uint32_t>();
     A.meta = pl->L_meta.as<uint32_t>();
     A.inlist = pl->L_inlist.as<uint32_t>();
+    A.twin = pl->L_twin.as<uint32_t>();
+    A.fdst = pl->L_fdst.as<int32_t>();
+    A.bmat = pl->L_bmat.as<double>();
     A.scr = pl->L_scr.as<double>();
     A.q = pl->L_q.as<double>();
     A.node = pl->L_node.as<uint32_t>();

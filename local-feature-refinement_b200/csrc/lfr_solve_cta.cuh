@@ -23,7 +23,7 @@ namespace lfr {
 struct CtaComp {
   uint32_t slot, Nc, Ec, nf;
   uint64_t e_off, n_off, f_off;  // offsets of this component in the per-edge / per-node / per-free-node arrays
-  uint32_t comp_index, pad;      // ordinal among the large components ((Nc + 1)-sized arrays)
+  uint32_t comp_index, regular;  // ordinal among the large components; 1 = every kept edge has exactly one twin
 };
 
 struct CtaArrays {
@@ -31,6 +31,9 @@ struct CtaArrays {
   const uint32_t* eidx;    // global edge index
   const uint32_t* meta;    // src_local | dst_local << 14 | kind << 28
   const uint32_t* inlist;  // kept-edge indices sorted by destination
+  const uint32_t* twin;    // index of the reverse edge (regular components)
+  const int32_t* fdst;     // free index of the edge's destination node, or -1
+  double* bmat;            // 4 doubles per edge: scaled off-diagonal block S_s H_sd S_d (regular components)
   double* scr;             // 7 doubles per edge (a, r0, r1, m00, m01, m10, m11), SoA per component
   double* q;               // 2 doubles per edge (matvec scratch)
   // per node
@@ -48,13 +51,16 @@ struct CtaArrays {
 
 constexpr int kCtaThreads = 256;
 enum { V_G = 0, V_S, V_DL, V_D2, V_R, V_Z, V_P, V_W, V_Y, V_COUNT };  // 2-doubles-per-node vectors
-// then two 3-doubles-per-node arrays: diagonal blocks (d00, d01, d11) and their damped inverses
+// then three 3-doubles-per-node arrays: diagonal blocks (d00, d01, d11), their damped scaled form, its inverse
 
 struct CtaCtx {
   int tid, Nc, Ec, nf, n;
   const uint32_t *eidx, *meta, *inlist, *node, *outptr, *inptr, *lof;
   const int32_t* freeof;
-  double *scr, *q, *x, *xc, *g, *S, *dl, *D2, *r, *z, *p, *w, *y, *diag, *pinv;
+  double *scr, *q, *x, *xc, *g, *S, *dl, *D2, *r, *z, *p, *w, *y, *diag, *pinv, *pblk, *bmat;
+  const uint32_t* twin;
+  const int32_t* fdst;
+  bool regular;
   const float4* edges;
   double* red;  // shared: 3 * 8 doubles
 };
@@ -171,7 +177,27 @@ __device__ __forceinline__ double cta_assemble(const CtaCtx& C, bool first, cons
     block_sum3(C, acc, z1, z2);
     return acc;
   }
-  return block_max(C, gmax);
+  gmax = block_max(C, gmax);  // (also makes S visible to every thread)
+  if (C.regular) {
+    // block-CSR form of S H S: one scaled 2x2 block per out-edge, edge + twin combined
+    for (int j = C.tid; j < C.Ec; j += kCtaThreads) {
+      const uint32_t mt = C.meta[j];
+      const int fs = C.freeof[mt & 0x3fff], fd = C.fdst[j];
+      if (fs < 0 || fd < 0) continue;
+      const uint32_t t = C.twin[j];
+      const double a = C.scr[j], at = C.scr[t];
+      const double m00 = C.scr[3 * E + j], m01 = C.scr[4 * E + j], m10 = C.scr[5 * E + j], m11 = C.scr[6 * E + j];
+      const double t00 = C.scr[3 * E + t], t01 = C.scr[4 * E + t], t10 = C.scr[5 * E + t], t11 = C.scr[6 * E + t];
+      const double s0 = C.S[2 * fs], s1 = C.S[2 * fs + 1], d0 = C.S[2 * fd], d1 = C.S[2 * fd + 1];
+      double* b = C.bmat + 4 * (size_t)j;  // block (s, d) = -a M^T - a_t M_t
+      b[0] = s0 * (-a * m00 - at * t00) * d0;
+      b[1] = s0 * (-a * m10 - at * t01) * d1;
+      b[2] = s1 * (-a * m01 - at * t10) * d0;
+      b[3] = s1 * (-a * m11 - at * t11) * d1;
+    }
+    __syncthreads();
+  }
+  return gmax;
 }
 
 // w = (S H S + D^2) v, matrix-free.
@@ -217,6 +243,32 @@ __device__ __forceinline__ void cta_matvec(const CtaCtx& C, const double* v, dou
   __syncthreads();
 }
 
+// Regular components: w = (S H S + D^2) v in ONE node-parallel pass over the
+// block-CSR rows (damped diagonal block `pblk` + one 2x2 block per out-edge);
+// returns this thread's share of v . w.
+__device__ __forceinline__ double cta_matvec_bcsr(const CtaCtx& C, const double* v, double* w, const double* pblk) {
+  double dot = 0.0;
+  for (int f = C.tid; f < C.nf; f += kCtaThreads) {
+    const int l = C.lof[f];
+    const double v0 = v[2 * f], v1 = v[2 * f + 1];
+    double a0 = pblk[3 * f] * v0 + pblk[3 * f + 1] * v1, a1 = pblk[3 * f + 1] * v0 + pblk[3 * f + 2] * v1;
+#pragma unroll 4
+    for (uint32_t j = C.outptr[l]; j < C.outptr[l + 1]; ++j) {
+      const int fd = C.fdst[j];
+      if (fd < 0) continue;
+      const double* b = C.bmat + 4 * (size_t)j;
+      const double u0 = v[2 * fd], u1 = v[2 * fd + 1];
+      a0 += b[0] * u0 + b[1] * u1;
+      a1 += b[2] * u0 + b[3] * u1;
+    }
+    w[2 * f] = a0;
+    w[2 * f + 1] = a1;
+    dot += v0 * a0 + v1 * a1;
+  }
+  __syncthreads();
+  return dot;
+}
+
 // Block-Jacobi PCG for (S H S + D^2) y = S g; dl = -S y.  Returns validity and
 // {model_cost_change, g . dl, |dl|_inf}.
 __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, const DevConsts& K, double* model_change,
@@ -235,6 +287,9 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
     const double det = p00 * p11 - h01 * h01;
     if (!(det > 0.0) || !(p00 > 0.0)) bad = 1.0;
     const double id = 1.0 / det;
+    C.pblk[3 * f] = p00;
+    C.pblk[3 * f + 1] = h01;
+    C.pblk[3 * f + 2] = p11;
     C.pinv[3 * f] = p11 * id;
     C.pinv[3 * f + 1] = -h01 * id;
     C.pinv[3 * f + 2] = p00 * id;
@@ -258,9 +313,13 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
   int it = 0;
   if (ok && bb > 0.0) {
     for (; it < max_it; ++it) {
-      cta_matvec(C, C.p, C.w);
       double pw = 0.0, z1 = 0.0, z2 = 0.0;
-      for (int i = C.tid; i < C.n; i += kCtaThreads) pw += C.p[i] * C.w[i];
+      if (C.regular) {
+        pw = cta_matvec_bcsr(C, C.p, C.w, C.pblk);
+      } else {
+        cta_matvec(C, C.p, C.w);
+        for (int i = C.tid; i < C.n; i += kCtaThreads) pw += C.p[i] * C.w[i];
+      }
       block_sum3(C, pw, z1, z2);
       if (!(pw > 0.0) || !isfinite(pw)) {  // not positive definite in working precision
         ok = false;
@@ -295,7 +354,7 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
   *cg_iters += (unsigned)it;
   if (diag_mode && ok && bb > 0.0) {  // LFR_PROFILE: true residual |b - A y| / |b| of the returned solution
     if (it >= max_it) ++*n_maxit;
-    cta_matvec(C, C.y, C.w);
+    if (C.regular) cta_matvec_bcsr(C, C.y, C.w, C.pblk); else cta_matvec(C, C.y, C.w);
     double e2 = 0.0, z1 = 0.0, z2 = 0.0;
     for (int i = C.tid; i < C.n; i += kCtaThreads) {
       const double d = C.S[i] * C.g[i] - C.w[i];
@@ -362,11 +421,18 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
   C.D2 = v0 + V_D2 * stride;
   C.r = v0 + V_R * stride;
   C.z = v0 + V_Z * stride;
-  C.p = v0 + V_P * stride;
+  C.p = v0 + V_P * stride;  // (replaced by shared memory below when it fits)
   C.w = v0 + V_W * stride;
   C.y = v0 + V_Y * stride;
   C.diag = A.vec + V_COUNT * stride + 3 * cc.f_off;
-  C.pinv = A.vec + V_COUNT * stride + 3 * A.total_free + 3 * cc.f_off;
+  C.pblk = A.vec + V_COUNT * stride + 3 * A.total_free + 3 * cc.f_off;
+  C.pinv = A.vec + V_COUNT * stride + 6 * A.total_free + 3 * cc.f_off;
+  C.bmat = A.bmat + 4 * cc.e_off;
+  C.twin = A.twin + cc.e_off;
+  C.fdst = A.fdst + cc.e_off;
+  C.regular = cc.regular != 0;
+  __shared__ double psh[4096];  // the CG search direction is the randomly-gathered vector: keep it on chip
+  if (C.n <= 4096) C.p = psh;
   C.edges = P.edges;
   C.red = red;
   const uint32_t c = cc.slot;

@@ -11,6 +11,18 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the C-ABI library is a build artefact (git-ignored): build it when a fresh checkout has none
+    # and nvcc is around (cross-compiles without a GPU); on the GPU box the shipped .so is used as is
+    so = os.path.join(ROOT, "local-feature-refinement_b200", "csrc", "liblfr_b200.so")
+    if not os.path.exists(so):
+        import importlib.util
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            spec = importlib.util.spec_from_file_location(
+                "lfr_csrc_build", os.path.join(ROOT, "local-feature-refinement_b200", "csrc", "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
 
 
 @pytest.fixture(scope="session")

@@ -106,6 +106,11 @@ def test_duplicate_pairs_take_the_serial_assembly_path(b200, oracle):
     p = build_problem(both)
     assert p.graph.n_edges == 2 * (ms.n_matches + dup.n_matches)
     _compare(b200, oracle, p)
+    # the CTA tier's two-phase matvec (no block-CSR without clean twins)
+    pos_g, st_g = b200.solve(p, b200.default_options(linear_solver=2))
+    pos_o, st_o = oracle.solve(p, oracle.default_options(n_threads=1))
+    assert np.abs(pos_g - pos_o).max() <= TOL_UNITS
+    assert np.array_equal(st_g["iterations"], st_o["iterations"])
 
 
 def test_cta_pcg_tier_on_large_components(b200, oracle):
