@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "liblfr_b200.so")
 SOURCES = ["lfr_capi.cu", "lfr_wire.cc", "lfr_host.cc"]
-DEPS = SOURCES + ["lfr_solve_warp.cuh", "lfr_solve_warp2.cuh", "lfr_solve_cta.cuh", "lfr_math.cuh", os.path.join("..", "..", "include", "lfr.h"),
+DEPS = SOURCES + ["lfr_solve_warp.cuh", "lfr_solve_warp2.cuh", "lfr_solve_cta.cuh", "lfr_solve_tile.cuh", "lfr_math.cuh", os.path.join("..", "..", "include", "lfr.h"),
                   os.path.join("..", "..", "include", "lfr_wire.h"),
                   os.path.join("..", "..", "include", "lfr_host.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

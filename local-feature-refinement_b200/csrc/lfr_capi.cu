@@ -10,7 +10,7 @@
 #include <vector>
 
 #include "lfr_solve_cta.cuh"
-#include "lfr_solve_warp2.cuh"
+#include "lfr_solve_tile.cuh"
 
 namespace {
 
@@ -203,8 +203,10 @@ int upload(DevBuf* d, const T* h, size_t count, cudaStream_t s) {
 int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   static const int kClass[] = {2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 57344, kMaxSmemPerBlock};
   const int n_class = sizeof(kClass) / sizeof(kClass[0]);
-  static const int kVariant[5] = {8, 16, 24, 32, 0};
-  const int kNV = 5;
+  // register warp kernel (8..32), register tile kernel (48, 64: 64 threads; 80: 128 threads), smem-Cholesky warp kernel (0)
+  static const int kVariant[8] = {8, 16, 24, 32, 48, 64, 80, 0};
+  const int kNV = 8;
+  const bool no_tile = getenv("LFR_NO_TILE") != nullptr;
   std::vector<std::vector<uint32_t>> members(kNV * n_class);
   std::vector<Bucket> caps(kNV * n_class);
   pl->comp_size.resize(p->n_components);
@@ -237,9 +239,11 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       continue;
     }
     const int e = std::max<int>(1, (int)eup);
-    int vi = (n2 <= 8) ? 0 : (n2 <= 16 ? 1 : (n2 <= 24 ? 2 : (n2 <= 32 ? 3 : 4)));
-    if (force_v1) vi = 4;
-    const int need = (vi == 4) ? lfr::WarpLayout(e, (int)nc, n2).total : lfr::Warp2Layout(e, (int)nc, n2).total;
+    int vi = (n2 <= 8) ? 0 : (n2 <= 16 ? 1 : (n2 <= 24 ? 2 : (n2 <= 32 ? 3 : (n2 <= 48 ? 4 : (n2 <= 64 ? 5 : (n2 <= 80 ? 6 : 7))))));
+    if (vi >= 4 && vi <= 6 && (no_tile || lfr::TileLayout(e, (int)nc, n2).total > kMaxSmemPerBlock)) vi = 7;
+    if (force_v1) vi = 7;
+    const int need = (vi == 7) ? lfr::WarpLayout(e, (int)nc, n2).total
+                     : (vi >= 4 ? lfr::TileLayout(e, (int)nc, n2).total : lfr::Warp2Layout(e, (int)nc, n2).total);
     int k = 0;
     while (k < n_class && need > kClass[k]) ++k;
     if (k == n_class) return fail(LFR_EUNSUPPORTED, "component needs more shared memory than one SM has");
@@ -257,11 +261,13 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       b.variant = kVariant[vi];
       b.n = (uint32_t)mem.size();
       b.offset = (uint32_t)pl->list_host.size();
-      b.smem_per_warp = (vi == 4) ? lfr::WarpLayout(b.emax, b.ncmax, b.n2max).total
-                                  : lfr::Warp2Layout(b.emax, b.ncmax, b.n2max).total;
+      b.smem_per_warp = (vi == 7) ? lfr::WarpLayout(b.emax, b.ncmax, b.n2max).total
+                        : (vi >= 4 ? lfr::TileLayout(b.emax, b.ncmax, b.n2max).total
+                                   : lfr::Warp2Layout(b.emax, b.ncmax, b.n2max).total);
       if (b.smem_per_warp > kMaxSmemPerBlock) return fail(LFR_EUNSUPPORTED, "bucket exceeds shared memory");
       b.warps = (4 * b.smem_per_warp <= kMaxSmemPerBlock) ? 4 : 1;
-      if (b.warps == 1 && b.variant != 0) b.variant = 32;  // only <1,32> is instantiated for single-warp CTAs
+      if (b.variant >= 48) b.warps = 1;  // tile kernels: one component per CTA
+      if (b.warps == 1 && b.variant != 0 && b.variant < 48) b.variant = 32;  // only <1,32> is instantiated for single-warp CTAs
       pl->list_host.insert(pl->list_host.end(), mem.begin(), mem.end());
       pl->buckets.push_back(b);
     }
@@ -464,6 +470,12 @@ int set_kernel_attrs() {
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp2_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_tile_kernel<64, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_tile_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_tile_kernel<128, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
   done_for_device = dev;
   return LFR_OK;
 }
@@ -522,7 +534,13 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
     wb.smem_per_warp = b.smem_per_warp;
     const size_t smem = (size_t)b.smem_per_warp * b.warps;
     const unsigned grid = (b.n + b.warps - 1) / b.warps;
-    if (b.variant == 8)
+    if (b.variant == 48)
+      lfr::solve_tile_kernel<64, 48><<<b.n, 64, smem, bs>>>(P, pl->K, wb);
+    else if (b.variant == 64)
+      lfr::solve_tile_kernel<64, 64><<<b.n, 64, smem, bs>>>(P, pl->K, wb);
+    else if (b.variant == 80)
+      lfr::solve_tile_kernel<128, 80><<<b.n, 128, smem, bs>>>(P, pl->K, wb);
+    else if (b.variant == 8)
       lfr::solve_warp2_kernel<4, 8><<<grid, 128, smem, bs>>>(P, pl->K, wb);
     else if (b.variant == 16)
       lfr::solve_warp2_kernel<4, 16><<<grid, 128, smem, bs>>>(P, pl->K, wb);
