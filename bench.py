@@ -245,6 +245,9 @@ def run_b200(args):
     _, st = plan.download(stream)
     alg_bytes, one_pass = plan.traffic(stream)
     launches = plan.num_launches()
+    # clocks are sampled over warm-up + the device-timed region; nvidia-smi polling stalls the host
+    # for tens of ms now and then, which the host-timed e2e leg below would pick up
+    clocks = sampler.stop() if sampler else None
     # ---- e2e: C-ABI call with pinned host buffers ------------------------------------------
     s2, keep, pos_pinned, h2d = pinned_problem(lib, p)
     stt, bufs = lib.make_stats(p.n_components)
@@ -263,11 +266,11 @@ def run_b200(args):
         if i >= args.warmup:
             e2e_t.append(dt)
             e2e_parts.append((stt.h2d_ms, stt.kernel_ms, stt.d2h_ms))
-    e2e_ms = 1e3 * float(np.mean(e2e_t))
+    e2e_ms = 1e3 * float(np.median(e2e_t))   # host wall clock: median over the K steps (robust to host jitter)
+    e2e_ms_mean = 1e3 * float(np.mean(e2e_t))
     if os.environ.get("LFR_BENCH_DEBUG"):
         sys.stderr.write("e2e steps ms: %s\nparts: %s\n" % ([round(1e3 * x, 3) for x in e2e_t], [[round(y, 3) for y in x] for x in e2e_parts]))
     e2e_break = [float(x) for x in np.mean(np.array(e2e_parts), axis=0)]
-    clocks = sampler.stop() if sampler else None
     # ---- reduce over ranks --------------------------------------------------------------------
     tot_tracks, tot_iters, tot_alg = n_tracks, int(st["total_iterations"]), alg_bytes
     if world > 1:
@@ -309,7 +312,7 @@ def run_b200(args):
         "lm_iters_per_s": tot_iters / (ms_per_step / 1e3),
         "ms_per_step_median": ms_per_step_median,
         "e2e": {"value": tot_tracks / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "ms_per_step_median": 1e3 * float(np.median(e2e_t)),
+                "ms_per_step_mean": e2e_ms_mean, "timing": "host wall clock around the call, median of K steps",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": "lfr_solve() (include/lfr.h) with pinned host buffers",
                 "stages_ms": {"h2d_and_schedule": e2e_break[0], "kernels": e2e_break[1], "d2h": e2e_break[2]}},

@@ -131,8 +131,20 @@ struct lfr_plan {
   uint32_t N = 0, C = 0;
   uint64_t E = 0;
   uint32_t total_slots = 0;
-  DevBuf row_ptr, edges, track, comp, is_root, comp_ptr, comp_nodes, local_of, pos, pos_init, iter, term, cost0,
-      cost1, ls, kept, cycles, lists, err;
+  DevBuf row_ptr, edges, track, comp, is_root, comp_ptr, comp_nodes, local_of, pos, pos_init, stats, cycles, lists;
+  // `stats` is one block (one memset, one D2H copy): cost0[Cp] cost1[Cp] iter[Cp] term[Cp] ls[Cp] kept[Cp] err[2]
+  uint32_t Cp = 0;               // C rounded up to an even count
+  bool pos_is_staged = false;    // lfr_solve(): the start point was uploaded straight into `pos`
+  void* h_stage = nullptr;       // pinned host staging for the stats block
+  size_t h_stage_cap = 0;
+  double* d_cost0() const { return stats.as<double>(); }
+  double* d_cost1() const { return stats.as<double>() + Cp; }
+  int32_t* d_iter() const { return reinterpret_cast<int32_t*>(stats.as<double>() + 2 * (size_t)Cp); }
+  int32_t* d_term() const { return d_iter() + Cp; }
+  uint32_t* d_ls() const { return reinterpret_cast<uint32_t*>(d_term() + Cp); }
+  uint32_t* d_kept() const { return d_ls() + Cp; }
+  int* d_err() const { return reinterpret_cast<int*>(d_kept() + Cp); }
+  size_t stats_bytes() const { return 16 * (size_t)Cp + 16 * (size_t)Cp + 8; }
   std::vector<Bucket> buckets;
   std::vector<uint32_t> comp_size;  // nodes per dispatch slot
   std::vector<uint32_t> list_host;
@@ -159,14 +171,14 @@ struct lfr_plan {
     P.comp_nodes = comp_nodes.as<uint32_t>();
     P.local_of = local_of.as<uint32_t>();
     P.positions = pos.as<double>();
-    P.st_iter = iter.as<int32_t>();
-    P.st_term = term.as<int32_t>();
-    P.st_cost0 = cost0.as<double>();
-    P.st_cost1 = cost1.as<double>();
-    P.st_ls = ls.as<uint32_t>();
-    P.st_kept = kept.as<uint32_t>();
+    P.st_iter = d_iter();
+    P.st_term = d_term();
+    P.st_cost0 = d_cost0();
+    P.st_cost1 = d_cost1();
+    P.st_ls = d_ls();
+    P.st_kept = d_kept();
     P.st_cycles = profile ? cycles.as<unsigned long long>() : nullptr;
-    P.err_flag = err.as<int>();
+    P.err_flag = d_err();
     return P;
   }
 };
@@ -176,11 +188,11 @@ namespace {
 void free_plan(lfr_plan* pl) {
   if (!pl) return;
   DevBuf* bufs[] = {&pl->row_ptr, &pl->edges, &pl->track, &pl->comp, &pl->is_root, &pl->comp_ptr, &pl->comp_nodes,
-                    &pl->local_of, &pl->pos, &pl->pos_init, &pl->iter, &pl->term, &pl->cost0, &pl->cost1, &pl->ls,
-                    &pl->kept, &pl->cycles, &pl->lists, &pl->err, &pl->L_comps, &pl->L_eidx, &pl->L_meta,
+                    &pl->local_of, &pl->pos, &pl->pos_init, &pl->stats, &pl->cycles, &pl->lists, &pl->L_comps, &pl->L_eidx, &pl->L_meta,
                     &pl->L_inlist, &pl->L_twin, &pl->L_fdst, &pl->L_bmat, &pl->L_scr, &pl->L_q, &pl->L_node, &pl->L_outptr, &pl->L_inptr, &pl->L_freeof,
                     &pl->L_x, &pl->L_xc, &pl->L_lof, &pl->L_vec};
   for (DevBuf* b : bufs) b->release();
+  if (pl->h_stage) cudaFreeHost(pl->h_stage);
   for (int i = 0; i < pl->n_streams; ++i) {
     if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
     if (pl->ev_join[i]) cudaEventDestroy(pl->ev_join[i]);
@@ -391,7 +403,7 @@ int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
 
 // (Re)fill a plan from host arrays: H2D copies + schedule.  Buffers only grow.
 int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const double* initial_positions,
-              cudaStream_t s) {
+              cudaStream_t s, bool stage_positions_directly = false) {
   pl->opt = o;
   pl->K = make_consts(o);
   pl->N = p->n_nodes;
@@ -409,28 +421,26 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
   const size_t N = std::max<size_t>(pl->N, 1), C = std::max<size_t>(pl->C, 1);
   LFR_TRY(pl->local_of.reserve(sizeof(uint32_t) * N));
   LFR_TRY(pl->pos.reserve(sizeof(double) * 2 * N));
-  LFR_TRY(pl->pos_init.reserve(sizeof(double) * 2 * N));
-  LFR_TRY(pl->iter.reserve(sizeof(int32_t) * C));
-  LFR_TRY(pl->term.reserve(sizeof(int32_t) * C));
-  LFR_TRY(pl->cost0.reserve(sizeof(double) * C));
-  LFR_TRY(pl->cost1.reserve(sizeof(double) * C));
-  LFR_TRY(pl->ls.reserve(sizeof(uint32_t) * C));
-  LFR_TRY(pl->kept.reserve(sizeof(uint32_t) * C));
-  LFR_TRY(pl->err.reserve(sizeof(int)));
+  pl->Cp = (uint32_t)((C + 1) & ~(size_t)1);
+  LFR_TRY(pl->stats.reserve(pl->stats_bytes()));
   if (pl->profile) LFR_TRY(pl->cycles.reserve(sizeof(unsigned long long) * 8 * C));
-  // per-slot stats default to "skipped" (size-1 components never run)
-  LFR_CUDA(cudaMemsetAsync(pl->iter.p, 0, sizeof(int32_t) * C, s));
-  LFR_CUDA(cudaMemsetAsync(pl->term.p, 0, sizeof(int32_t) * C, s));
-  LFR_CUDA(cudaMemsetAsync(pl->cost0.p, 0, sizeof(double) * C, s));
-  LFR_CUDA(cudaMemsetAsync(pl->cost1.p, 0, sizeof(double) * C, s));
-  LFR_CUDA(cudaMemsetAsync(pl->ls.p, 0, sizeof(uint32_t) * C, s));
-  LFR_CUDA(cudaMemsetAsync(pl->kept.p, 0, sizeof(uint32_t) * C, s));
-  LFR_CUDA(cudaMemsetAsync(pl->err.p, 0, sizeof(int), s));
-  if (initial_positions && pl->N)
-    LFR_CUDA(cudaMemcpyAsync(pl->pos_init.p, initial_positions, sizeof(double) * 2 * (size_t)pl->N,
-                             cudaMemcpyHostToDevice, s));
-  else
-    LFR_CUDA(cudaMemsetAsync(pl->pos_init.p, 0, sizeof(double) * 2 * N, s));
+  // per-slot stats default to "skipped" (size-1 components never run); also clears the error flag
+  LFR_CUDA(cudaMemsetAsync(pl->stats.p, 0, pl->stats_bytes(), s));
+  if (stage_positions_directly) {
+    // lfr_solve(): the caller's start point goes straight into the working array
+    if (pl->N)
+      LFR_CUDA(cudaMemcpyAsync(pl->pos.p, initial_positions, sizeof(double) * 2 * (size_t)pl->N,
+                               cudaMemcpyHostToDevice, s));
+    pl->pos_is_staged = true;
+  } else {
+    LFR_TRY(pl->pos_init.reserve(sizeof(double) * 2 * N));
+    if (initial_positions && pl->N)
+      LFR_CUDA(cudaMemcpyAsync(pl->pos_init.p, initial_positions, sizeof(double) * 2 * (size_t)pl->N,
+                               cudaMemcpyHostToDevice, s));
+    else
+      LFR_CUDA(cudaMemsetAsync(pl->pos_init.p, 0, sizeof(double) * 2 * N, s));
+    pl->pos_is_staged = false;
+  }
   LFR_TRY(build_buckets(pl, p));  // host work overlaps the copies above
   LFR_TRY(prepare_large(pl, p, s));
   LFR_TRY(upload(&pl->lists, pl->list_host.data(), pl->list_host.size(), s));
@@ -482,9 +492,10 @@ int set_kernel_attrs() {
 
 int launch_solve(lfr_plan* pl, cudaStream_t s) {
   LFR_TRY(set_kernel_attrs());
-  if (pl->N)
+  if (pl->N && !pl->pos_is_staged)
     LFR_CUDA(cudaMemcpyAsync(pl->pos.p, pl->pos_init.p, sizeof(double) * 2 * (size_t)pl->N,
                              cudaMemcpyDeviceToDevice, s));
+  pl->pos_is_staged = false;  // a second launch on the same plan needs the reset again
   const lfr::DevProblem P = pl->dev();
   const int nb = (int)pl->buckets.size();
   const int n_side = std::max(0, nb - 1) + ((pl->n_large && nb > 0) ? 1 : 0);
@@ -566,31 +577,37 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
 int download(lfr_plan* pl, cudaStream_t s, double* positions, lfr_stats* st) {
   if (positions && pl->N)
     LFR_CUDA(cudaMemcpyAsync(positions, pl->pos.p, sizeof(double) * 2 * (size_t)pl->N, cudaMemcpyDeviceToHost, s));
-  std::vector<int32_t> it;
-  std::vector<uint32_t> ls;
-  int err = 0;
-  LFR_CUDA(cudaMemcpyAsync(&err, pl->err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  if (st && pl->C) {
-    it.resize(pl->C);
-    ls.resize(pl->C);
-    LFR_CUDA(cudaMemcpyAsync(it.data(), pl->iter.p, sizeof(int32_t) * pl->C, cudaMemcpyDeviceToHost, s));
-    LFR_CUDA(cudaMemcpyAsync(ls.data(), pl->ls.p, sizeof(uint32_t) * pl->C, cudaMemcpyDeviceToHost, s));
-    if (st->termination)
-      LFR_CUDA(cudaMemcpyAsync(st->termination, pl->term.p, sizeof(int32_t) * pl->C, cudaMemcpyDeviceToHost, s));
-    if (st->initial_cost)
-      LFR_CUDA(cudaMemcpyAsync(st->initial_cost, pl->cost0.p, sizeof(double) * pl->C, cudaMemcpyDeviceToHost, s));
-    if (st->final_cost)
-      LFR_CUDA(cudaMemcpyAsync(st->final_cost, pl->cost1.p, sizeof(double) * pl->C, cudaMemcpyDeviceToHost, s));
+  const size_t nb = pl->stats_bytes();
+  if (pl->h_stage_cap < nb) {
+    if (pl->h_stage) cudaFreeHost(pl->h_stage);
+    pl->h_stage = nullptr;
+    pl->h_stage_cap = 0;
+    LFR_CUDA(cudaMallocHost(&pl->h_stage, nb + nb / 4));
+    pl->h_stage_cap = nb + nb / 4;
   }
+  LFR_CUDA(cudaMemcpyAsync(pl->h_stage, pl->stats.p, nb, cudaMemcpyDeviceToHost, s));
   LFR_CUDA(cudaStreamSynchronize(s));
+  const size_t Cp = pl->Cp;
+  const double* h_cost0 = static_cast<const double*>(pl->h_stage);
+  const double* h_cost1 = h_cost0 + Cp;
+  const int32_t* h_iter = reinterpret_cast<const int32_t*>(h_cost1 + Cp);
+  const int32_t* h_term = h_iter + Cp;
+  const uint32_t* h_ls = reinterpret_cast<const uint32_t*>(h_term + Cp);
+  const uint32_t* h_kept = h_ls + Cp;
+  const int err = *reinterpret_cast<const int*>(h_kept + Cp);
   if (err) return fail(LFR_EINVAL, "edge with dst out of range or a self edge (found while staging edges on the device)");
   if (st) {
     uint64_t ti = 0, tl = 0;
     for (uint32_t c = 0; c < pl->C; ++c) {
-      ti += (uint64_t)it[c];
-      tl += ls[c];
+      ti += (uint64_t)h_iter[c];
+      tl += h_ls[c];
     }
-    if (st->iterations && pl->C) std::memcpy(st->iterations, it.data(), sizeof(int32_t) * pl->C);
+    if (pl->C) {
+      if (st->iterations) std::memcpy(st->iterations, h_iter, sizeof(int32_t) * pl->C);
+      if (st->termination) std::memcpy(st->termination, h_term, sizeof(int32_t) * pl->C);
+      if (st->initial_cost) std::memcpy(st->initial_cost, h_cost0, sizeof(double) * pl->C);
+      if (st->final_cost) std::memcpy(st->final_cost, h_cost1, sizeof(double) * pl->C);
+    }
     st->total_iterations = ti;
     st->total_line_search_steps = tl;
     st->n_solved = pl->n_solved;
@@ -700,13 +717,11 @@ int lfr_plan_traffic(lfr_plan* pl, void* stream, uint64_t* algorithmic_bytes, ui
   if (!pl) return fail(LFR_EINVAL, "plan is NULL");
   LFR_CUDA(cudaSetDevice(pl->device));
   cudaStream_t s = (cudaStream_t)stream;
-  std::vector<int32_t> it(pl->C);
-  std::vector<uint32_t> kept(pl->C);
-  if (pl->C) {
-    LFR_CUDA(cudaMemcpyAsync(it.data(), pl->iter.p, sizeof(int32_t) * pl->C, cudaMemcpyDeviceToHost, s));
-    LFR_CUDA(cudaMemcpyAsync(kept.data(), pl->kept.p, sizeof(uint32_t) * pl->C, cudaMemcpyDeviceToHost, s));
-  }
+  std::vector<unsigned char> blk(pl->stats_bytes());
+  LFR_CUDA(cudaMemcpyAsync(blk.data(), pl->stats.p, blk.size(), cudaMemcpyDeviceToHost, s));
   LFR_CUDA(cudaStreamSynchronize(s));
+  const int32_t* it = reinterpret_cast<const int32_t*>(blk.data() + 16 * (size_t)pl->Cp);
+  const uint32_t* kept = reinterpret_cast<const uint32_t*>(blk.data() + 16 * (size_t)pl->Cp + 12 * (size_t)pl->Cp);
   uint64_t alg = 0, one = 0;
   for (uint32_t c = 0; c < pl->C; ++c) {
     if (pl->comp_size[c] <= 1) continue;
@@ -752,7 +767,7 @@ int lfr_solve(const lfr_problem* p, const lfr_options* opt, double* positions, l
   lfr_plan* pl = ws.plan[o.device];
   cudaStream_t s = 0;
   LFR_CUDA(cudaEventRecord(ws.ev[0], s));
-  LFR_TRY(fill_plan(pl, p, o, positions, s));
+  LFR_TRY(fill_plan(pl, p, o, positions, s, /*stage_positions_directly=*/true));
   LFR_CUDA(cudaEventRecord(ws.ev[1], s));
   LFR_TRY(launch_solve(pl, s));
   LFR_CUDA(cudaEventRecord(ws.ev[2], s));
