@@ -54,11 +54,12 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def ncu_traffic():
-    """DRAM bytes per step of the solve kernels from the committed ncu capture, or None."""
+def ncu_traffic(workload):
+    """DRAM bytes per step of the solve kernels from the committed ncu capture of this
+    workload (profiles/traffic.json), or None when none was taken."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh).get("dram_bytes_per_step")
+            return json.load(fh).get("dram_bytes_per_step", {}).get(workload)
     except Exception:
         return None
 
@@ -179,10 +180,13 @@ def run_reference(args):
             _, st = orc.solve(q, o)
             iters += st["total_iterations"]
         t.append(time.perf_counter() - t0)
-    ms = 1e3 * float(np.mean(t))
+    # median of the K steps: the host-side pool is sensitive to other tenants of the box; the median
+    # is the conservative (faster) reading of the reference
+    ms = 1e3 * float(np.median(t))
     value = n_tracks / (ms / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "ms_per_step_mean": 1e3 * float(np.mean(t)),
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, p, n_tracks),
             "lm_iters_per_s": iters / (ms / 1e3),
@@ -318,7 +322,7 @@ def run_b200(args):
                 "stages_ms": {"h2d_and_schedule": e2e_break[0], "kernels": e2e_break[1], "d2h": e2e_break[2]}},
         "gpu_launches": int(launches * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(),
+                     "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                      "peak_source": "%s HBM copy bandwidth (burst)" % peak_src,
                      "algorithmic_bytes_per_step": int(alg_bytes), "one_pass_bytes": int(one_pass),
                      "kernel": "solve_warp_kernel (all size buckets of one step)"},
