@@ -77,7 +77,11 @@ def main(argv=None) -> int:
         # the reference parses zero files and writes an empty solution
         pass
     try:
-        ms = wire.read_matching_file(args.matches_file) if wire.matches_files(args.matches_file) else None
+        if args.matches_file.endswith(".npz") and os.path.exists(args.matches_file):
+            from .matchset import MatchSet
+            ms = MatchSet.load_npz(args.matches_file)   # packed arrays written by MatchSet.save_npz (opt-in extra)
+        else:
+            ms = wire.read_matching_file(args.matches_file) if wire.matches_files(args.matches_file) else None
     except wire.ParseError:
         sys.stderr.write("Failed to parse proto object.\n")
         return 255

@@ -54,6 +54,27 @@ class MatchSet:
         assert self.disp1.dtype == np.float32 and self.disp2.dtype == np.float32
         assert self.sim.dtype == np.float32
 
+    # ---- packed on-disk form (the producer can emit this next to,
+    # or instead of, the protobuf and skip serialise -> parse) --------------------
+    def save_npz(self, path: str) -> None:
+        """Write the flat arrays as one .npz (fp32 flows, exactly the wire content)."""
+        np.savez(path, image_names=np.array(self.image_names, dtype=object), pair_img1=self.pair_img1,
+                 pair_img2=self.pair_img2, pair_fact1=self.pair_fact1, pair_fact2=self.pair_fact2,
+                 pair_ptr=self.pair_ptr, feat1=self.feat1, feat2=self.feat2, sim=self.sim, disp1=self.disp1,
+                 disp2=self.disp2)
+
+    @staticmethod
+    def load_npz(path: str) -> "MatchSet":
+        z = np.load(path, allow_pickle=True)
+        ms = MatchSet(image_names=[str(x) for x in z["image_names"].tolist()],
+                      pair_img1=z["pair_img1"].astype(np.int64), pair_img2=z["pair_img2"].astype(np.int64),
+                      pair_fact1=z["pair_fact1"].astype(np.float32), pair_fact2=z["pair_fact2"].astype(np.float32),
+                      pair_ptr=z["pair_ptr"].astype(np.int64), feat1=z["feat1"].astype(np.uint32),
+                      feat2=z["feat2"].astype(np.uint32), sim=z["sim"].astype(np.float32),
+                      disp1=z["disp1"].astype(np.float32), disp2=z["disp2"].astype(np.float32))
+        ms.validate()
+        return ms
+
     def without_images(self, banned) -> "MatchSet":
         """Drop every pair touching a banned image (solve.cc:444-446)."""
         banned = set(banned)
