@@ -305,6 +305,9 @@ def run_b200(args):
         cpu_t.append(time.perf_counter() - t1)
     reps = len(cpu_t)
     cpu_ms = 1e3 * float(np.median(cpu_t))   # median: robust to host-side noise at start-up
+    t1 = time.perf_counter()
+    orc.solve(p, orc.default_options(n_threads=1))   # per-core figure
+    cpu_1t_ms = 1e3 * (time.perf_counter() - t1)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -327,7 +330,8 @@ def run_b200(args):
                      "algorithmic_bytes_per_step": int(alg_bytes), "one_pass_bytes": int(one_pass),
                      "kernel": "solve_warp_kernel (all size buckets of one step)"},
         "cpu_baseline": {"value": n_tracks / (cpu_ms / 1e3), "unit": UNIT, "cores": cores, "kind": "port",
-                         "ms_per_step": cpu_ms,
+                         "ms_per_step": cpu_ms, "single_thread_value": n_tracks / (cpu_1t_ms / 1e3),
+                         "single_thread_ms_per_step": cpu_1t_ms,
                          "sample": "whole workload x %d repetitions (Ceres-1.14-semantics CPU oracle, "
                                    "oracle/lfr_oracle.cc)" % reps},
         "clocks": clocks,
