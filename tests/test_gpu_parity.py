@@ -215,6 +215,58 @@ def test_malformed_edges_are_reported(b200):
     assert st["n_solved"] > 0
 
 
+def test_option_variants(b200, oracle):
+    """Non-default options travel through the ABI: iteration cap (NO_CONVERGENCE),
+    tight tolerances, a smaller box, other loss widths."""
+    _, p = get_problem("cfg1")
+    for opts in (dict(max_num_iterations=2), dict(function_tolerance=1e-10, parameter_tolerance=1e-10),
+                 dict(bound=0.2), dict(cauchy_a=0.1, tukey_a=0.2), dict(initial_trust_region_radius=1.0),
+                 dict(min_relative_decrease=0.6)):
+        pos_g, st_g = b200.solve(p, b200.default_options(**opts))
+        pos_o, st_o = oracle.solve(p, oracle.default_options(n_threads=2, **opts))
+        assert np.abs(pos_g - pos_o).max() <= TOL_UNITS, opts
+        np.testing.assert_array_equal(st_g["iterations"], st_o["iterations"], err_msg=str(opts))
+        np.testing.assert_array_equal(st_g["termination"], st_o["termination"], err_msg=str(opts))
+    _, st = b200.solve(p, b200.default_options(max_num_iterations=2))
+    assert (st["termination"] == 5).any()           # LFR_TERM_NO_CONVERGENCE
+    pos, _ = b200.solve(p, b200.default_options(bound=0.2))
+    assert np.abs(pos).max() <= 0.2
+
+
+def test_active_bounds_and_clamped_grids(b200, oracle):
+    """Flows three times larger than the box: solutions sit on the +-1 bounds and
+    many evaluations happen in the clamped region of the interpolator."""
+    from lfr_b200 import build_problem, synth
+    ms = synth.generate("cfg2", scale=0.05, seed=12)
+    ms.disp1 *= 3.0
+    ms.disp2 *= 3.0
+    p = build_problem(ms)
+    err, st = _compare(b200, oracle, p)
+    pos, _ = b200.solve(p)
+    assert (np.abs(pos) == 1.0).sum() > 10
+
+
+@pytest.mark.parametrize("seed", [101, 202, 303, 404, 505, 606])
+def test_seed_fuzz(b200, oracle, seed):
+    """Small random scenes of every family (exhaustive, sequential, ring)."""
+    from lfr_b200 import build_problem, synth
+    for cfg, scale in (("cfg2", 0.04), ("cfg4", 0.04), ("ring60", 0.3)):
+        p = build_problem(synth.generate(cfg, scale=scale, seed=seed))
+        pos_g, st_g = b200.solve(p)
+        pos_o, st_o = oracle.solve(p, oracle.default_options(n_threads=8))
+        sizes = np.diff(p.comp_ptr.astype(np.int64))
+        err = np.zeros(p.n_components)
+        for c in range(p.n_components):
+            nodes = p.comp_nodes[p.comp_ptr[c]:p.comp_ptr[c + 1]].astype(int)
+            err[c] = np.abs(pos_g[nodes] - pos_o[nodes]).max()
+        good = (err <= TOL_UNITS) & (st_g["iterations"] == st_o["iterations"])
+        nfree = np.array([int((~p.is_root[p.comp_nodes[p.comp_ptr[c]:p.comp_ptr[c + 1]].astype(int)].astype(bool)).sum())
+                          for c in range(p.n_components)])
+        exact_tier = 2 * nfree <= 96           # register / Cholesky tiers: exact solves, must match everywhere
+        assert good[exact_tier].all(), (cfg, seed, err[exact_tier].max())
+        assert good.mean() >= 0.98, (cfg, seed)  # PCG tier: see test_cta_pcg_tier_up_to_400_unknowns
+
+
 def test_plan_resolve_is_deterministic(b200):
     """Row-owned sums, no atomics: re-running the plan is bit-identical."""
     from lfr_b200.capi import Plan
