@@ -357,111 +357,16 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   C.lof = (uint16_t*)(base + L.lof);
   C.edges = P.edges;
 
-  const uint32_t nbeg = P.comp_ptr[c];
-  const int Nc = (int)(P.comp_ptr[c + 1] - nbeg);
+  const int Nc = (int)(P.comp_ptr[c + 1] - P.comp_ptr[c]);
   C.Nc = Nc;
-  // ---- setup by warp 0 (solve.cc:98-143), identical to the warp kernel ---------------------
+  // ---- setup by warp 0 (solve.cc:98-143), shared with the warp kernel -----------------------
   if (tid < 32) {
-    int run = 0;
-    for (int l0 = 0; l0 < Nc; l0 += 32) {
-      const int l = l0 + lane;
-      int d = 0;
-      if (l < Nc) {
-        const uint32_t v = P.comp_nodes[nbeg + l];
-        const uint32_t rs = P.row_ptr[v];
-        d = (int)(P.row_ptr[v + 1] - rs);
-        C.node[l] = v;
-        rowstart[l] = rs;
-        cnt[l] = 0;
-        cnt[B.ncmax + l] = 0;
-        double p0 = P.positions[2 * (size_t)v], p1 = P.positions[2 * (size_t)v + 1];
-        if (!P.is_root[v]) {
-          p0 = fmin(fmax(p0, -K.bound), K.bound);
-          p1 = fmin(fmax(p1, -K.bound), K.bound);
-        }
-        C.x[2 * l] = p0;
-        C.x[2 * l + 1] = p1;
-      }
-      const int inc = warp_incl_scan(d, lane);
-      if (l < Nc) candptr[l] = run + inc - d;
-      run += __shfl_sync(kFull, inc, 31);
-    }
-    if (lane == 0) candptr[Nc] = run;
-    __syncwarp();
-    const int Eup = run;
-    int kept = 0;
-    for (int k0 = 0; k0 < Eup; k0 += 32) {
-      const int k = k0 + lane;
-      bool keep = false;
-      uint32_t e = 0, mt = 0;
-      if (k < Eup) {
-        int lo = 0, hi = Nc - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if ((int)candptr[mid] <= k) lo = mid; else hi = mid - 1;
-        }
-        e = rowstart[lo] + (uint32_t)(k - (int)candptr[lo]);
-        const uint32_t v = C.node[lo];
-        const uint32_t dst = __float_as_uint(__ldg(&P.edges[5 * (size_t)e + 4].w));
-        if (dst >= P.n_nodes || dst == v) {
-          *P.err_flag = 1;
-        } else {
-          int kind = LFR_EDGE_SKIP;
-          if (P.track[v] == P.track[dst]) kind = LFR_EDGE_CAUCHY;
-          else if (P.comp[v] == P.comp[dst]) kind = LFR_EDGE_TUKEY;
-          keep = (kind != LFR_EDGE_SKIP) && !(P.is_root[v] && P.is_root[dst]);
-          if (keep) {
-            const uint32_t dl_ = P.local_of[dst];
-            mt = (uint32_t)lo | (dl_ << 12) | ((uint32_t)kind << 24);
-            atomicAdd(&cnt[lo], 1);
-            atomicAdd(&cnt[B.ncmax + dl_], 1);
-          }
-        }
-      }
-      const unsigned m = __ballot_sync(kFull, keep);
-      if (keep) {
-        const int pos = kept + __popc(m & ((1u << lane) - 1u));
-        C.eidx[pos] = e;
-        C.meta[pos] = mt;
-      }
-      kept += __popc(m);
-    }
-    __syncwarp();
-    const int Ec = kept;
-    int orun = 0, frun = 0;
-    for (int l0 = 0; l0 < Nc; l0 += 32) {
-      const int l = l0 + lane;
-      const int co = (l < Nc) ? cnt[l] : 0, ci = (l < Nc) ? cnt[B.ncmax + l] : 0;
-      const int so = warp_incl_scan(co, lane);
-      const bool is_free = (l < Nc) && (co + ci > 0) && !P.is_root[C.node[l < Nc ? l : 0]];
-      const int sf = warp_incl_scan(is_free ? 1 : 0, lane);
-      if (l < Nc) {
-        C.outptr[l] = (uint16_t)(orun + so - co);
-        C.freeof[l] = is_free ? (int16_t)(frun + sf - 1) : (int16_t)-1;
-        if (is_free) C.lof[frun + sf - 1] = (uint16_t)l;
-      }
-      orun += __shfl_sync(kFull, so, 31);
-      frun += __shfl_sync(kFull, sf, 31);
-    }
-    if (lane == 0) C.outptr[Nc] = (uint16_t)orun;
-    __syncwarp();
+    int Ec = 0, nf = 0;
     bool irregular = false;
-    for (int e = lane; e < Ec; e += 32) {
-      const uint32_t mt = C.meta[e];
-      const int s = mt & 0xfff, d = (mt >> 12) & 0xfff;
-      int found = 0, tw = e;
-      for (int j = C.outptr[d]; j < C.outptr[d + 1]; ++j)
-        if ((int)((C.meta[j] >> 12) & 0xfff) == s) {
-          tw = j;
-          ++found;
-        }
-      irregular = irregular || (found != 1);
-      C.twin[e] = (uint16_t)tw;
-    }
-    irregular = __any_sync(kFull, irregular);
+    warp_setup(C, rowstart, candptr, cnt, B.ncmax, P, K, c, lane, &Ec, &nf, &irregular);
     if (lane == 0) {
       hdr[0] = Ec;
-      hdr[1] = frun;
+      hdr[1] = nf;
       hdr[2] = irregular ? 1 : 0;
       P.st_kept[c] = (uint32_t)Ec;
     }

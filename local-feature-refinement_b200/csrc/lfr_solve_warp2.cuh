@@ -329,6 +329,120 @@ __device__ __forceinline__ void make_candidate2(const Warp2Ctx& C, double alpha,
   __syncwarp();
 }
 
+// Component setup by ONE warp (solve.cc:98-143): node list and start point,
+// compaction of the kept out-edges (same track -> Cauchy, same component ->
+// Tukey, other component or root-root -> dropped) with ballots, out-edge ranges,
+// free-variable numbering, and the twin (reverse edge) of every kept edge.
+// Shared by the warp kernel and the tile kernel (whose warp 0 runs it).
+template <class Ctx>
+__device__ __forceinline__ void warp_setup(Ctx& C, uint32_t* rowstart, uint32_t* candptr, int* cnt, int ncmax,
+                                           const DevProblem& P, const DevConsts& K, uint32_t c, int lane,
+                                           int* Ec_out, int* nf_out, bool* irregular_out) {
+  const uint32_t nbeg = P.comp_ptr[c];
+  const int Nc = (int)(P.comp_ptr[c + 1] - nbeg);
+  C.Nc = Nc;
+  int run = 0;
+  for (int l0 = 0; l0 < Nc; l0 += 32) {
+    const int l = l0 + lane;
+    int d = 0;
+    if (l < Nc) {
+      const uint32_t v = P.comp_nodes[nbeg + l];
+      const uint32_t rs = P.row_ptr[v];
+      d = (int)(P.row_ptr[v + 1] - rs);
+      C.node[l] = v;
+      rowstart[l] = rs;
+      cnt[l] = 0;
+      cnt[ncmax + l] = 0;
+      double p0 = P.positions[2 * (size_t)v], p1 = P.positions[2 * (size_t)v + 1];
+      if (!P.is_root[v]) {  // IterationZero: x <- Plus(x, 0) projects the start point
+        p0 = fmin(fmax(p0, -K.bound), K.bound);
+        p1 = fmin(fmax(p1, -K.bound), K.bound);
+      }
+      C.x[2 * l] = p0;
+      C.x[2 * l + 1] = p1;
+    }
+    const int inc = warp_incl_scan(d, lane);
+    if (l < Nc) candptr[l] = run + inc - d;
+    run += __shfl_sync(kFull, inc, 31);
+  }
+  if (lane == 0) candptr[Nc] = run;
+  __syncwarp();
+  const int Eup = run;
+  int kept = 0;
+  for (int k0 = 0; k0 < Eup; k0 += 32) {
+    const int k = k0 + lane;
+    bool keep = false;
+    uint32_t e = 0, mt = 0;
+    if (k < Eup) {
+      int lo = 0, hi = Nc - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)candptr[mid] <= k) lo = mid; else hi = mid - 1;
+      }
+      e = rowstart[lo] + (uint32_t)(k - (int)candptr[lo]);
+      const uint32_t v = C.node[lo];
+      const uint32_t dst = __float_as_uint(__ldg(&P.edges[5 * (size_t)e + 4].w));
+      if (dst >= P.n_nodes || dst == v) {
+        *P.err_flag = 1;  // malformed input: reported by the host as LFR_EINVAL
+      } else {
+        int kind = LFR_EDGE_SKIP;
+        if (P.track[v] == P.track[dst]) kind = LFR_EDGE_CAUCHY;          // solve.cc:105
+        else if (P.comp[v] == P.comp[dst]) kind = LFR_EDGE_TUKEY;        // solve.cc:114
+        keep = (kind != LFR_EDGE_SKIP) && !(P.is_root[v] && P.is_root[dst]);
+        if (keep) {
+          const uint32_t dl_ = P.local_of[dst];
+          mt = (uint32_t)lo | (dl_ << 12) | ((uint32_t)kind << 24);
+          atomicAdd(&cnt[lo], 1);              // kept out-degree (integer: order-independent)
+          atomicAdd(&cnt[ncmax + dl_], 1);   // kept in-degree
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(kFull, keep);
+    if (keep) {
+      const int pos = kept + __popc(m & ((1u << lane) - 1u));
+      C.eidx[pos] = e;
+      C.meta[pos] = mt;
+    }
+    kept += __popc(m);
+  }
+  __syncwarp();
+  const int Ec = kept;
+  int orun = 0, frun = 0;
+  for (int l0 = 0; l0 < Nc; l0 += 32) {
+    const int l = l0 + lane;
+    const int co = (l < Nc) ? cnt[l] : 0, ci = (l < Nc) ? cnt[ncmax + l] : 0;
+    const int so = warp_incl_scan(co, lane);
+    const bool is_free = (l < Nc) && (co + ci > 0) && !P.is_root[C.node[l < Nc ? l : 0]];
+    const int sf = warp_incl_scan(is_free ? 1 : 0, lane);
+    if (l < Nc) {
+      C.outptr[l] = (uint16_t)(orun + so - co);
+      C.freeof[l] = is_free ? (int16_t)(frun + sf - 1) : (int16_t)-1;
+      if (is_free) C.lof[frun + sf - 1] = (uint16_t)l;
+    }
+    orun += __shfl_sync(kFull, so, 31);
+    frun += __shfl_sync(kFull, sf, 31);
+  }
+  if (lane == 0) C.outptr[Nc] = (uint16_t)orun;
+  __syncwarp();
+  // twin of every kept edge: the unique kept edge dst -> src
+  bool irregular = false;
+  for (int e = lane; e < Ec; e += 32) {
+    const uint32_t mt = C.meta[e];
+    const int s = mt & 0xfff, d = (mt >> 12) & 0xfff;
+    int found = 0, tw = e;
+    for (int j = C.outptr[d]; j < C.outptr[d + 1]; ++j)
+      if ((int)((C.meta[j] >> 12) & 0xfff) == s) {
+        tw = j;
+        ++found;
+      }
+    irregular = irregular || (found != 1);
+    C.twin[e] = (uint16_t)tw;
+  }
+  *irregular_out = __any_sync(kFull, irregular);
+  *Ec_out = Ec;
+  *nf_out = frun;
+}
+
 template <int WARPS, int NREG>
 __global__ void __launch_bounds__(WARPS * 32, (NREG > 16 ? 8 : 12) / WARPS)
 solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
@@ -371,108 +485,13 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
 #define LFR_TICK(acc) do { if (prof) { const long long now__ = clock64(); acc += now__ - t_mark; t_mark = now__; } } while (0)
 
   // ---- component setup (solve.cc:98-143) --------------------------------------
-  const uint32_t nbeg = P.comp_ptr[c];
-  const int Nc = (int)(P.comp_ptr[c + 1] - nbeg);
-  C.Nc = Nc;
-  int run = 0;
-  for (int l0 = 0; l0 < Nc; l0 += 32) {
-    const int l = l0 + lane;
-    int d = 0;
-    if (l < Nc) {
-      const uint32_t v = P.comp_nodes[nbeg + l];
-      const uint32_t rs = P.row_ptr[v];
-      d = (int)(P.row_ptr[v + 1] - rs);
-      C.node[l] = v;
-      rowstart[l] = rs;
-      cnt[l] = 0;
-      cnt[B.ncmax + l] = 0;
-      double p0 = P.positions[2 * (size_t)v], p1 = P.positions[2 * (size_t)v + 1];
-      if (!P.is_root[v]) {  // IterationZero: x <- Plus(x, 0) projects the start point
-        p0 = fmin(fmax(p0, -K.bound), K.bound);
-        p1 = fmin(fmax(p1, -K.bound), K.bound);
-      }
-      C.x[2 * l] = p0;
-      C.x[2 * l + 1] = p1;
-    }
-    const int inc = warp_incl_scan(d, lane);
-    if (l < Nc) candptr[l] = run + inc - d;
-    run += __shfl_sync(kFull, inc, 31);
-  }
-  if (lane == 0) candptr[Nc] = run;
-  __syncwarp();
-  const int Eup = run;
-  int kept = 0;
-  for (int k0 = 0; k0 < Eup; k0 += 32) {
-    const int k = k0 + lane;
-    bool keep = false;
-    uint32_t e = 0, mt = 0;
-    if (k < Eup) {
-      int lo = 0, hi = Nc - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if ((int)candptr[mid] <= k) lo = mid; else hi = mid - 1;
-      }
-      e = rowstart[lo] + (uint32_t)(k - (int)candptr[lo]);
-      const uint32_t v = C.node[lo];
-      const uint32_t dst = __float_as_uint(__ldg(&P.edges[5 * (size_t)e + 4].w));
-      if (dst >= P.n_nodes || dst == v) {
-        *P.err_flag = 1;  // malformed input: reported by the host as LFR_EINVAL
-      } else {
-        int kind = LFR_EDGE_SKIP;
-        if (P.track[v] == P.track[dst]) kind = LFR_EDGE_CAUCHY;          // solve.cc:105
-        else if (P.comp[v] == P.comp[dst]) kind = LFR_EDGE_TUKEY;        // solve.cc:114
-        keep = (kind != LFR_EDGE_SKIP) && !(P.is_root[v] && P.is_root[dst]);
-        if (keep) {
-          const uint32_t dl_ = P.local_of[dst];
-          mt = (uint32_t)lo | (dl_ << 12) | ((uint32_t)kind << 24);
-          atomicAdd(&cnt[lo], 1);              // kept out-degree (integer: order-independent)
-          atomicAdd(&cnt[B.ncmax + dl_], 1);   // kept in-degree
-        }
-      }
-    }
-    const unsigned m = __ballot_sync(kFull, keep);
-    if (keep) {
-      const int pos = kept + __popc(m & ((1u << lane) - 1u));
-      C.eidx[pos] = e;
-      C.meta[pos] = mt;
-    }
-    kept += __popc(m);
-  }
-  __syncwarp();
-  const int Ec = kept;
+  int Ec = 0, nf_setup = 0;
+  bool irregular_setup = false;
+  warp_setup(C, rowstart, candptr, cnt, B.ncmax, P, K, c, lane, &Ec, &nf_setup, &irregular_setup);
   C.Ec = Ec;
-  int orun = 0, frun = 0;
-  for (int l0 = 0; l0 < Nc; l0 += 32) {
-    const int l = l0 + lane;
-    const int co = (l < Nc) ? cnt[l] : 0, ci = (l < Nc) ? cnt[B.ncmax + l] : 0;
-    const int so = warp_incl_scan(co, lane);
-    const bool is_free = (l < Nc) && (co + ci > 0) && !P.is_root[C.node[l < Nc ? l : 0]];
-    const int sf = warp_incl_scan(is_free ? 1 : 0, lane);
-    if (l < Nc) {
-      C.outptr[l] = (uint16_t)(orun + so - co);
-      C.freeof[l] = is_free ? (int16_t)(frun + sf - 1) : (int16_t)-1;
-      if (is_free) C.lof[frun + sf - 1] = (uint16_t)l;
-    }
-    orun += __shfl_sync(kFull, so, 31);
-    frun += __shfl_sync(kFull, sf, 31);
-  }
-  if (lane == 0) C.outptr[Nc] = (uint16_t)orun;
-  __syncwarp();
-  // twin of every kept edge: the unique kept edge dst -> src
-  bool irregular = false;
-  for (int e = lane; e < Ec; e += 32) {
-    const uint32_t mt = C.meta[e];
-    const int s = mt & 0xfff, d = (mt >> 12) & 0xfff;
-    int found = 0, tw = e;
-    for (int j = C.outptr[d]; j < C.outptr[d + 1]; ++j)
-      if ((int)((C.meta[j] >> 12) & 0xfff) == s) {
-        tw = j;
-        ++found;
-      }
-    irregular = irregular || (found != 1);
-    C.twin[e] = (uint16_t)tw;
-  }
-  C.irregular = __any_sync(kFull, irregular);
+  C.irregular = irregular_setup;
+  const int Nc = C.Nc;
+  const int frun = nf_setup;
   const int nf = frun;
   C.nf = nf;
   C.n = 2 * nf;
