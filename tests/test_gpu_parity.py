@@ -267,6 +267,28 @@ def test_seed_fuzz(b200, oracle, seed):
         assert good.mean() >= 0.98, (cfg, seed)  # PCG tier: see test_cta_pcg_tier_up_to_400_unknowns
 
 
+def test_sharded_multi_gpu_solve_is_bitwise_identical(tmp_path):
+    """`solve --gpus 2` (one rank per GPU, NCCL all-reduce of disjoint position
+    slices) writes the same SolutionFile bytes as one GPU.  Needs 2 devices."""
+    import os
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run tools/gpu_dist_check.py under gpurun --gpus 2)")
+    from lfr_b200 import synth, wire
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    m = str(tmp_path / "m.pb")
+    wire.write_matching_file(synth.generate("cfg2", scale=0.2), m)
+    outs = []
+    for g in (1, 2):
+        o = str(tmp_path / ("s%d.pb" % g))
+        r = subprocess.run([os.path.join(root, "multi-view-refinement", "build", "solve"), "--matches_file", m,
+                            "--output_file", o, "--gpus", str(g)], capture_output=True, text=True, cwd=root)
+        assert r.returncode == 0, r.stderr
+        outs.append(open(o, "rb").read())
+    assert outs[0] == outs[1] and len(outs[0]) > 0
+
+
 def test_plan_resolve_is_deterministic(b200):
     """Row-owned sums, no atomics: re-running the plan is bit-identical."""
     from lfr_b200.capi import Plan
