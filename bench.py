@@ -83,47 +83,105 @@ def workload_config(name, p, n_tracks, extra=None):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region.  The region is tens of
+    milliseconds, so the primary sampler is an NVML thread (pynvml, ~2 ms period);
+    `nvidia-smi -lms` is the fallback when NVML cannot be opened."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.sm, self.reasons, self.smax = [], set(), None
+        self.p = self.f = self.thread = None
+        self.source = "none"
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps cuda indices; resolve through the PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(device).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(device), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(nv.nvmlDeviceGetCount()):
+                    hh = nv.nvmlDeviceGetHandleByIndex(i)
+                    if nv.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        h = hh
+                        break
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(device)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+
+            def run():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for nm, bit in names:
+                            if r & bit:
+                                self.reasons.add(nm)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self.thread = threading.Thread(target=run, daemon=True)
+            self.source = "nvml thread, 2 ms period"
         except Exception:
-            self.p = None
+            self.thread = None
+            try:
+                self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                           "--format=csv,noheader,nounits", "-lms", "20"],
+                                          stdout=self.f, stderr=subprocess.DEVNULL)
+                self.source = "nvidia-smi -lms 20"
+                time.sleep(0.5)   # nvidia-smi needs a few hundred ms before its first line
+            except Exception:
+                self.p = None
+
+    def start(self):
+        """Call right before the timed region (the warm-up has already loaded the GPU)."""
+        if self.thread is not None:
+            self.thread.start()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, smax, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            sm, smax = self.sm, ([self.smax] if self.smax else [])
+        elif self.p is not None:
+            self.p.terminate()
             try:
-                sm.append(float(c[1]))
-                smax.append(float(c[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.f.name)
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+            self.f.flush()
+            self.f.seek(0)
+            sm, smax = [], []
+            for line in self.f.read().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    smax.append(float(c[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 c[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            os.unlink(self.f.name)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
         return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(smax)) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "sm_max_mhz": float(max(smax)) if smax else None, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.source}
 
 
 def pinned_problem(lib, p):
@@ -234,6 +292,8 @@ def run_b200(args):
         plan.solve(stream)
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     # ---- value: device-resident, CUDA events per step ---------------------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -249,8 +309,8 @@ def run_b200(args):
     _, st = plan.download(stream)
     alg_bytes, one_pass = plan.traffic(stream)
     launches = plan.num_launches()
-    # clocks are sampled over warm-up + the device-timed region; nvidia-smi polling stalls the host
-    # for tens of ms now and then, which the host-timed e2e leg below would pick up
+    # clocks are sampled over the device-timed region only; the sampler stops before the host-timed
+    # e2e leg so that its polling cannot perturb it
     clocks = sampler.stop() if sampler else None
     # ---- e2e: C-ABI call with pinned host buffers ------------------------------------------
     s2, keep, pos_pinned, h2d = pinned_problem(lib, p)
@@ -274,7 +334,7 @@ def run_b200(args):
     e2e_ms_mean = 1e3 * float(np.mean(e2e_t))
     if os.environ.get("LFR_BENCH_DEBUG"):
         sys.stderr.write("e2e steps ms: %s\nparts: %s\n" % ([round(1e3 * x, 3) for x in e2e_t], [[round(y, 3) for y in x] for x in e2e_parts]))
-    e2e_break = [float(x) for x in np.mean(np.array(e2e_parts), axis=0)]
+    e2e_break = [float(x) for x in np.median(np.array(e2e_parts), axis=0)]   # medians, like e2e_ms
     # ---- reduce over ranks --------------------------------------------------------------------
     tot_tracks, tot_iters, tot_alg = n_tracks, int(st["total_iterations"]), alg_bytes
     if world > 1:

@@ -256,6 +256,126 @@ __device__ __noinline__ int real_roots_in(const double* c, int n, double lo, dou
   return segment_roots(p, 5, crit[0], crit[1], crit[2], ncrit, lo, hi, out, lane);
 }
 
+// ---- fixed-degree variants ----------------------------------------------------
+// The same operations in the same order as the generic routines above, with the
+// sizes known at compile time so that every coefficient and root stays in a
+// register (the generic ones index small arrays dynamically -> local memory on
+// the critical path of every Newton step).  Used when no leading coefficient
+// vanishes; the generic routines remain the fallback.
+template <int N>
+__device__ __forceinline__ void horner2_n(const double (&q)[N], double x, double* f, double* df) {
+  double v = q[0], d = 0.0;
+#pragma unroll
+  for (int i = 1; i < N; ++i) {
+    d = d * x + v;
+    v = v * x + q[i];
+  }
+  *f = v;
+  *df = d;
+}
+
+template <int N>
+__device__ __forceinline__ double poly_eval_n(const double (&p)[N], double x) {
+  double v = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) v = v * x + p[i];
+  return v;
+}
+
+template <int N>
+__device__ __forceinline__ double bracket_root_n(const double (&q)[N], double a, double b, double fa, double fb) {
+  if (fa == 0.0) return a;
+  if (fb == 0.0) return b;
+  double xl = fa < 0.0 ? a : b, xh = fa < 0.0 ? b : a;
+  double x = 0.5 * (a + b), dxold = fabs(b - a), dx = dxold, f, df;
+  horner2_n<N>(q, x, &f, &df);
+  for (int it = 0; it < 100; ++it) {
+    if ((((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
+      dxold = dx;
+      dx = 0.5 * (xh - xl);
+      x = xl + dx;
+      if (xl == x) return x;
+    } else {
+      dxold = dx;
+      dx = f / df;
+      const double t = x;
+      x -= dx;
+      if (t == x) return x;
+    }
+    if (fabs(dx) <= 1e-13 * fabs(x)) return x;
+    horner2_n<N>(q, x, &f, &df);
+    if (f < 0.0) xl = x; else xh = x;
+  }
+  return x;
+}
+
+// segment_roots with N coefficients and at most M segments (M = N - 2)
+template <int N, int M>
+__device__ __forceinline__ int segment_roots_n(const double (&q)[N], double b0, double b1, double b2, int nbrk,
+                                               double lo, double hi, double (&out)[M], int lane) {
+  bool has = false;
+  double r = 0.0;
+  if (lane <= nbrk) {
+    const double xa = lane == 0 ? lo : (lane == 1 ? b0 : (lane == 2 ? b1 : b2));
+    const double inner = lane == 0 ? b0 : (lane == 1 ? b1 : b2);
+    const double xb = (lane < nbrk) ? inner : hi;
+    double fa, fb, tmp;
+    horner2_n<N>(q, xa, &fa, &tmp);
+    horner2_n<N>(q, xb, &fb, &tmp);
+    has = ((fa <= 0.0 && fb >= 0.0) || (fa >= 0.0 && fb <= 0.0)) && !(fa == 0.0 && fb == 0.0);
+    if (has) r = bracket_root_n<N>(q, xa, xb, fa, fb);
+  }
+  int cnt = 0;
+  double last = 0.0;
+#pragma unroll
+  for (int s = 0; s < M; ++s) {
+    const int hs = __shfl_sync(0xffffffffu, (int)has, s);
+    const double rs = __shfl_sync(0xffffffffu, r, s);
+    if (s <= nbrk && hs && (cnt == 0 || rs != last)) {
+#pragma unroll
+      for (int k = 0; k < M; ++k)
+        if (cnt == k) out[k] = rs;
+      last = rs;
+      ++cnt;
+    }
+  }
+  return cnt;
+}
+
+// FindQuadraticPolynomialRoots, real case, a != 0; roots inside [lo, hi], ascending
+__device__ __forceinline__ int quadratic_roots_in(double a, double b, double cc, double lo, double hi, double* o0,
+                                                  double* o1) {
+  const double D = b * b - 4 * a * cc;
+  if (D < 0) return 0;
+  const double sq = sqrt(D);
+  double r0, r1;
+  if (b >= 0) {
+    r0 = (-b - sq) / (2.0 * a);
+    r1 = (2.0 * cc) / (-b - sq);
+  } else {
+    r0 = (2.0 * cc) / (-b + sq);
+    r1 = (-b + sq) / (2.0 * a);
+  }
+  if (r1 < r0) { const double t = r0; r0 = r1; r1 = t; }
+  int cnt = 0;
+  if (r0 >= lo && r0 <= hi) { *o0 = r0; cnt = 1; }
+  if (r1 >= lo && r1 <= hi && r1 != r0) {
+    if (cnt == 0) *o0 = r1; else *o1 = r1;
+    ++cnt;
+  }
+  return cnt;
+}
+
+// Real roots in [lo, hi] of the quartic q (q[0] != 0), ascending
+__device__ __forceinline__ int quartic_roots_in(const double (&q)[5], double lo, double hi, double (&out)[4], int lane) {
+  const double d3[4] = {4.0 * q[0], 3.0 * q[1], 2.0 * q[2], q[3]};
+  double c0 = 0.0, c1 = 0.0;
+  const int n2 = quadratic_roots_in(3.0 * d3[0], 2.0 * d3[1], d3[2], lo, hi, &c0, &c1);
+  double crit[3] = {0.0, 0.0, 0.0};
+  const int n3 = segment_roots_n<4, 3>(d3, c0, c1, 0.0, n2, lo, hi, crit, lane);
+  return segment_roots_n<5, 4>(q, crit[0], crit[1], crit[2], n3, lo, hi, out, lane);
+}
+
 // Minimiser over [lo, hi] (in x) of the Hermite interpolant through (0, f0, g0),
 // (x1, f1, g1) [and (x2, f2, g2) if three == true].  Warp-uniform.
 __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1, double f1, double g1,
@@ -322,6 +442,63 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
     nc = 6;
   }
   const double tlo = lo * ih, thi = hi * ih;
+  const double sx[3] = {0.0, x1, x2};
+  if (three && c[0] != 0.0) {
+    // quintic with a full-degree derivative: everything in registers
+    const double c6[6] = {c[0], c[1], c[2], c[3], c[4], c[5]};
+    double ox = (lo + hi) / 2.0;
+    double ov = poly_eval_n<6>(c6, ox * ih);
+    double v = poly_eval_n<6>(c6, tlo);
+    if (v < ov) { ov = v; ox = lo; }
+    v = poly_eval_n<6>(c6, thi);
+    if (v < ov) { ov = v; ox = hi; }
+    const double der4[5] = {5.0 * c6[0], 4.0 * c6[1], 3.0 * c6[2], 2.0 * c6[3], c6[4]};
+    double roots[4] = {0.0, 0.0, 0.0, 0.0};
+    const int nr = quartic_roots_in(der4, tlo, thi, roots, lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < nr && roots[i] >= tlo && roots[i] <= thi) {
+        v = poly_eval_n<6>(c6, roots[i]);
+        if (v < ov) { ov = v; ox = roots[i] * h; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (sx[i] >= lo && sx[i] <= hi) {
+        v = poly_eval_n<6>(c6, sx[i] * ih);
+        if (v < ov) { ov = v; ox = sx[i]; }
+      }
+    }
+    return ox;
+  }
+  if (!three && c[0] != 0.0) {
+    // cubic: the derivative is a quadratic with closed-form roots
+    const double c4[4] = {c[0], c[1], c[2], c[3]};
+    double ox = (lo + hi) / 2.0;
+    double ov = poly_eval_n<4>(c4, ox * ih);
+    double v = poly_eval_n<4>(c4, tlo);
+    if (v < ov) { ov = v; ox = lo; }
+    v = poly_eval_n<4>(c4, thi);
+    if (v < ov) { ov = v; ox = hi; }
+    double r0 = 0.0, r1 = 0.0;
+    const int nr = quadratic_roots_in(3.0 * c4[0], 2.0 * c4[1], c4[2], tlo, thi, &r0, &r1);
+    if (nr > 0) {
+      v = poly_eval_n<4>(c4, r0);
+      if (v < ov) { ov = v; ox = r0 * h; }
+    }
+    if (nr > 1) {
+      v = poly_eval_n<4>(c4, r1);
+      if (v < ov) { ov = v; ox = r1 * h; }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (sx[i] >= lo && sx[i] <= hi) {
+        v = poly_eval_n<4>(c4, sx[i] * ih);
+        if (v < ov) { ov = v; ox = sx[i]; }
+      }
+    }
+    return ox;
+  }
   // MinimizePolynomial: middle, ends, real parts of the roots of p'
   double ox = (lo + hi) / 2.0;
   double ov = poly_eval(c, nc, ox * ih);
@@ -339,7 +516,6 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
     if (v < ov) { ov = v; ox = roots[i] * h; }
   }
   // MinimizeInterpolatingPolynomial: the samples themselves, in order
-  const double sx[3] = {0.0, x1, x2};
   for (int i = 0; i < (three ? 3 : 2); ++i) {
     if (sx[i] < lo || sx[i] > hi) continue;
     v = poly_eval(c, nc, sx[i] * ih);
