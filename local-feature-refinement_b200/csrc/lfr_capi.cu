@@ -742,6 +742,18 @@ int lfr_debug_plan_cycles(lfr_plan* pl, unsigned long long* out) {
   return LFR_OK;
 }
 
+#ifdef LFR_POLY_PROF
+/* diagnostic build only: cycle split of the line-search polynomial (lfr_math.cuh) */
+int lfr_debug_poly_prof(unsigned long long* out16, int reset) {
+  LFR_CUDA(cudaMemcpyFromSymbol(out16, lfr::g_poly_prof, sizeof(unsigned long long) * 16));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    LFR_CUDA(cudaMemcpyToSymbol(lfr::g_poly_prof, z, sizeof(z)));
+  }
+  return LFR_OK;
+}
+#endif
+
 void lfr_plan_destroy(lfr_plan* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);

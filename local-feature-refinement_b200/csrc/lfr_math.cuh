@@ -116,8 +116,9 @@ __device__ __forceinline__ EdgeEval eval_edge(const float4 q[5], int kind, doubl
 // interval ends, real parts of all roots of p', and the sample abscissae.  The
 // same interpolant is built here in the normalised variable t = x / h
 // (h = largest sample step), where the two constraints at 0 fix the two lowest
-// coefficients and the rest is a 2x2 (cubic) or 4x4 (quintic) solve — the same
-// polynomial as Ceres' 4x4 / 6x6 Vandermonde solve, better conditioned.  Only
+// coefficients and the rest is a 2x2 (cubic) or 4x4 (quintic) system — the same
+// polynomial as Ceres' 4x4 / 6x6 Vandermonde solve, better conditioned (closed
+// forms: a 2x2 solve, or the divided differences of the reduced cubic).  Only
 // the real critical points inside the interval can win the minimisation, and
 // those are bracketed exactly (see real_roots_in).  oracle/lfr_oracle.cc
 // mirrors this operation for operation.
@@ -152,6 +153,16 @@ __device__ __forceinline__ void horner2(const double* q, int nq, double x, doubl
   *df = d;
 }
 
+// f / df for the Newton step: the correctly rounded single-precision reciprocal
+// of df (MUFU.RCP + fix-up, bit-identical to the oracle's 1.0f / (float)df) is
+// accurate enough to keep the quadratic convergence and replaces the double
+// division, the longest dependent chain of the iteration.
+__device__ __forceinline__ double newton_quotient(double f, double df) {
+  const double adf = fabs(df);
+  if (!(adf > 1e-30 && adf < 1e30)) return f / df;
+  return f * (double)__frcp_rn(__double2float_rn(df));
+}
+
 __device__ __forceinline__ double bracket_root(const double* q, int nq, double a, double b, double fa, double fb) {
   if (fa == 0.0) return a;
   if (fb == 0.0) return b;
@@ -166,12 +177,12 @@ __device__ __forceinline__ double bracket_root(const double* q, int nq, double a
       if (xl == x) return x;
     } else {
       dxold = dx;
-      dx = f / df;
+      dx = newton_quotient(f, df);
       const double t = x;
       x -= dx;
       if (t == x) return x;
     }
-    if (fabs(dx) <= 1e-13 * fabs(x)) return x;  // Newton converges quadratically: the next step would be ~1e-26
+    if (fabs(dx) <= 1e-8 * fabs(x)) return x;  // quadratic convergence: the error after this step is ~1e-16
     horner2(q, nq, x, &f, &df);
     if (f < 0.0) xl = x; else xh = x;
   }
@@ -256,6 +267,20 @@ __device__ __noinline__ int real_roots_in(const double* c, int n, double lo, dou
   return segment_roots(p, 5, crit[0], crit[1], crit[2], ncrit, lo, hi, out, lane);
 }
 
+#ifdef LFR_POLY_PROF
+// Diagnostic build only (-DLFR_POLY_PROF): cycle split of hermite_minimizer, read
+// back with lfr_debug_poly_prof().  [0] coefficients [1] first evaluations
+// [2] quadratic [3] cubic level [4] quartic level [5] final evaluations
+// [6] quintic calls [7] cubic calls [8] Newton iterations [9] bracket_root calls
+// [10] whole cubic-interpolant call
+__device__ unsigned long long g_poly_prof[16];
+#define LFR_PP_TICK(k) do { const long long n__ = clock64(); if (lane == 0) atomicAdd(&g_poly_prof[k], (unsigned long long)(n__ - pp_t)); pp_t = n__; } while (0)
+#define LFR_PP_COUNT(k) atomicAdd(&g_poly_prof[k], 1ull)
+#else
+#define LFR_PP_TICK(k) do {} while (0)
+#define LFR_PP_COUNT(k) do {} while (0)
+#endif
+
 // ---- fixed-degree variants ----------------------------------------------------
 // The same operations in the same order as the generic routines above, with the
 // sizes known at compile time so that every coefficient and root stays in a
@@ -289,7 +314,9 @@ __device__ __forceinline__ double bracket_root_n(const double (&q)[N], double a,
   double xl = fa < 0.0 ? a : b, xh = fa < 0.0 ? b : a;
   double x = 0.5 * (a + b), dxold = fabs(b - a), dx = dxold, f, df;
   horner2_n<N>(q, x, &f, &df);
+  LFR_PP_COUNT(9);
   for (int it = 0; it < 100; ++it) {
+    LFR_PP_COUNT(8);
     if ((((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
       dxold = dx;
       dx = 0.5 * (xh - xl);
@@ -297,12 +324,12 @@ __device__ __forceinline__ double bracket_root_n(const double (&q)[N], double a,
       if (xl == x) return x;
     } else {
       dxold = dx;
-      dx = f / df;
+      dx = newton_quotient(f, df);
       const double t = x;
       x -= dx;
       if (t == x) return x;
     }
-    if (fabs(dx) <= 1e-13 * fabs(x)) return x;
+    if (fabs(dx) <= 1e-8 * fabs(x)) return x;
     horner2_n<N>(q, x, &f, &df);
     if (f < 0.0) xl = x; else xh = x;
   }
@@ -367,13 +394,18 @@ __device__ __forceinline__ int quadratic_roots_in(double a, double b, double cc,
 }
 
 // Real roots in [lo, hi] of the quartic q (q[0] != 0), ascending
-__device__ __forceinline__ int quartic_roots_in(const double (&q)[5], double lo, double hi, double (&out)[4], int lane) {
+__device__ __forceinline__ int quartic_roots_in(const double (&q)[5], double lo, double hi, double (&out)[4], int lane,
+                                                long long& pp_t) {
   const double d3[4] = {4.0 * q[0], 3.0 * q[1], 2.0 * q[2], q[3]};
   double c0 = 0.0, c1 = 0.0;
   const int n2 = quadratic_roots_in(3.0 * d3[0], 2.0 * d3[1], d3[2], lo, hi, &c0, &c1);
+  LFR_PP_TICK(2);
   double crit[3] = {0.0, 0.0, 0.0};
   const int n3 = segment_roots_n<4, 3>(d3, c0, c1, 0.0, n2, lo, hi, crit, lane);
-  return segment_roots_n<5, 4>(q, crit[0], crit[1], crit[2], n3, lo, hi, out, lane);
+  LFR_PP_TICK(3);
+  const int n4 = segment_roots_n<5, 4>(q, crit[0], crit[1], crit[2], n3, lo, hi, out, lane);
+  LFR_PP_TICK(4);
+  return n4;
 }
 
 // Minimiser over [lo, hi] (in x) of the Hermite interpolant through (0, f0, g0),
@@ -381,6 +413,11 @@ __device__ __forceinline__ int quartic_roots_in(const double (&q)[5], double lo,
 __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1, double f1, double g1,
                                                  bool three, double x2, double f2, double g2, double lo,
                                                  double hi, int lane) {
+  long long pp_t = 0;
+#ifdef LFR_POLY_PROF
+  pp_t = clock64();
+  if (lane == 0) LFR_PP_COUNT(three ? 6 : 7);
+#endif
   const double h = three ? fmax(x1, x2) : x1;
   const double ih = 1.0 / h;  // the only division by h: t = x * ih
   const double g0h = g0 * h;
@@ -394,49 +431,24 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
     c[3] = f0;
     nc = 4;
   } else {
-    double A[4][5];
-    const double ts[2] = {x1 * ih, x2 * ih};
-    const double fs[2] = {f1, f2}, gs[2] = {g1, g2};
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const double t = ts[q], t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
-      A[2 * q][0] = t2; A[2 * q][1] = t3; A[2 * q][2] = t4; A[2 * q][3] = t5;
-      A[2 * q][4] = fs[q] - f0 - g0h * t;
-      A[2 * q + 1][0] = 2.0 * t; A[2 * q + 1][1] = 3.0 * t2; A[2 * q + 1][2] = 4.0 * t3; A[2 * q + 1][3] = 5.0 * t4;
-      A[2 * q + 1][4] = (gs[q] - g0) * h;
-    }
-    // Gaussian elimination with partial pivoting, fully unrolled (registers)
-    double ipiv[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-      for (int i = k + 1; i < 4; ++i) {
-        if (fabs(A[i][k]) > fabs(A[k][k])) {
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const double t = A[k][j];
-            A[k][j] = A[i][j];
-            A[i][j] = t;
-          }
-        }
-      }
-      ipiv[k] = 1.0 / A[k][k];  // one reciprocal per pivot
-#pragma unroll
-      for (int i = k + 1; i < 4; ++i) {
-        const double mlt = A[i][k] * ipiv[k];
-#pragma unroll
-        for (int j = k; j < 5; ++j) A[i][j] -= mlt * A[k][j];
-      }
-    }
-    double d[4];
-#pragma unroll
-    for (int i = 3; i >= 0; --i) {
-      double acc = A[i][4];
-#pragma unroll
-      for (int j = i + 1; j < 4; ++j) acc -= A[i][j] * d[j];
-      d[i] = acc * ipiv[i];
-    }
-    c[0] = d[3]; c[1] = d[2]; c[2] = d[1]; c[3] = d[0];
+    // p(t) = f0 + g0h t + t^2 s(t): s is the cubic Hermite interpolant of
+    // S = (p - f0 - g0h t) / t^2 and its derivative D at ta and tb, in Newton's
+    // divided differences, expanded to monomials: three independent reciprocals
+    // instead of the four dependent pivots of a 4x4 elimination
+    const double ta = x1 * ih, tb = x2 * ih;
+    const double ita = 1.0 / ta, itb = 1.0 / tb, iw = 1.0 / (tb - ta);
+    const double ita2 = ita * ita, itb2 = itb * itb;
+    const double Sa = (f1 - f0 - g0h * ta) * ita2;
+    const double Sb = (f2 - f0 - g0h * tb) * itb2;
+    const double Da = ((g1 - g0) * h - 2.0 * ta * Sa) * ita2;
+    const double Db = ((g2 - g0) * h - 2.0 * tb * Sb) * itb2;
+    const double m = (Sb - Sa) * iw;
+    const double e2 = (m - Da) * iw;
+    const double e3 = ((Db - m) - (m - Da)) * iw * iw;
+    c[0] = e3;
+    c[1] = e2 - e3 * (2.0 * ta + tb);
+    c[2] = Da + ta * (e3 * (ta + 2.0 * tb) - 2.0 * e2);
+    c[3] = Sa + ta * (ta * (e2 - e3 * tb) - Da);
     c[4] = g0h;
     c[5] = f0;
     nc = 6;
@@ -446,6 +458,7 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
   if (three && c[0] != 0.0) {
     // quintic with a full-degree derivative: everything in registers
     const double c6[6] = {c[0], c[1], c[2], c[3], c[4], c[5]};
+    LFR_PP_TICK(0);
     double ox = (lo + hi) / 2.0;
     double ov = poly_eval_n<6>(c6, ox * ih);
     double v = poly_eval_n<6>(c6, tlo);
@@ -454,7 +467,8 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
     if (v < ov) { ov = v; ox = hi; }
     const double der4[5] = {5.0 * c6[0], 4.0 * c6[1], 3.0 * c6[2], 2.0 * c6[3], c6[4]};
     double roots[4] = {0.0, 0.0, 0.0, 0.0};
-    const int nr = quartic_roots_in(der4, tlo, thi, roots, lane);
+    LFR_PP_TICK(1);
+    const int nr = quartic_roots_in(der4, tlo, thi, roots, lane, pp_t);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (i < nr && roots[i] >= tlo && roots[i] <= thi) {
@@ -469,6 +483,7 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
         if (v < ov) { ov = v; ox = sx[i]; }
       }
     }
+    LFR_PP_TICK(5);
     return ox;
   }
   if (!three && c[0] != 0.0) {
@@ -497,6 +512,7 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
         if (v < ov) { ov = v; ox = sx[i]; }
       }
     }
+    LFR_PP_TICK(10);
     return ox;
   }
   // MinimizePolynomial: middle, ends, real parts of the roots of p'

@@ -141,8 +141,8 @@ void loss_eval(int kind, double sim, double s, const lfr_options& o,
 // degree 2, eigenvalues of the balanced companion matrix above), and the sample
 // abscissae.  The restatement builds the SAME polynomial in the normalised
 // variable t = x / h (h = largest sample step): the two constraints at 0 fix
-// the two lowest coefficients, the others come from a 2x2 (closed form) or 4x4
-// (partial pivoting) solve; of the companion-matrix eigenvalues only the real
+// the two lowest coefficients, the others come from a 2x2 solve (closed form) or
+// from the divided differences of the reduced cubic; of the companion-matrix eigenvalues only the real
 // ones inside the interval can win the minimisation, and those are bracketed
 // exactly (real_roots_in).  csrc/lfr_math.cuh mirrors this operation for operation.
 // ---------------------------------------------------------------------------
@@ -176,6 +176,19 @@ void horner2(const double* q, int nq, double x, double* f, double* df) {
   *df = d;
 }
 
+// f / df for the Newton step.  The step only has to be accurate enough to keep
+// the quadratic convergence, so the quotient uses the correctly rounded SINGLE
+// precision reciprocal of df (relative error 2^-24; bit-identical on CPU and in
+// CUDA's __frcp_rn) instead of a double division, which is the longest
+// dependent chain of the iteration on the GPU.  Outside the safe single
+// precision range it is the plain division.
+double newton_quotient(double f, double df) {
+  const double adf = std::fabs(df);
+  if (!(adf > 1e-30 && adf < 1e30)) return f / df;
+  const float r = 1.0f / static_cast<float>(df);
+  return f * static_cast<double>(r);
+}
+
 double bracket_root(const double* q, int nq, double a, double b, double fa, double fb) {
   if (fa == 0.0) return a;
   if (fb == 0.0) return b;
@@ -190,12 +203,15 @@ double bracket_root(const double* q, int nq, double a, double b, double fa, doub
       if (xl == x) return x;
     } else {
       dxold = dx;
-      dx = f / df;
+      dx = newton_quotient(f, df);
       const double t = x;
       x -= dx;
       if (t == x) return x;
     }
-    if (std::fabs(dx) <= 1e-13 * std::fabs(x)) return x;  // Newton converges quadratically: the next step would be ~1e-26
+    // Newton converges quadratically: after a step of relative size <= 1e-8 the
+    // error is ~1e-16 (the 6e-8 relative error of newton_quotient only adds
+    // 6e-8 * 1e-8), so this is the last useful iteration
+    if (std::fabs(dx) <= 1e-8 * std::fabs(x)) return x;
     horner2(q, nq, x, &f, &df);
     if (f < 0.0) xl = x; else xh = x;
   }
@@ -288,35 +304,24 @@ double hermite_minimizer(double f0, double g0, double x1, double f1, double g1, 
     c[3] = f0;
     nc = 4;
   } else {
-    double A[4][5];
-    const double ts[2] = {x1 * ih, x2 * ih};
-    const double fs[2] = {f1, f2}, gs[2] = {g1, g2};
-    for (int q = 0; q < 2; ++q) {
-      const double t = ts[q], t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
-      A[2 * q][0] = t2; A[2 * q][1] = t3; A[2 * q][2] = t4; A[2 * q][3] = t5;
-      A[2 * q][4] = fs[q] - f0 - g0h * t;
-      A[2 * q + 1][0] = 2.0 * t; A[2 * q + 1][1] = 3.0 * t2; A[2 * q + 1][2] = 4.0 * t3;
-      A[2 * q + 1][3] = 5.0 * t4;
-      A[2 * q + 1][4] = (gs[q] - g0) * h;
-    }
-    double ipiv[4];
-    for (int k = 0; k < 4; ++k) {
-      for (int i = k + 1; i < 4; ++i)
-        if (std::fabs(A[i][k]) > std::fabs(A[k][k]))
-          for (int j = 0; j < 5; ++j) std::swap(A[k][j], A[i][j]);
-      ipiv[k] = 1.0 / A[k][k];  // one reciprocal per pivot
-      for (int i = k + 1; i < 4; ++i) {
-        const double mlt = A[i][k] * ipiv[k];
-        for (int j = k; j < 5; ++j) A[i][j] -= mlt * A[k][j];
-      }
-    }
-    double d[4];
-    for (int i = 3; i >= 0; --i) {
-      double acc = A[i][4];
-      for (int j = i + 1; j < 4; ++j) acc -= A[i][j] * d[j];
-      d[i] = acc * ipiv[i];
-    }
-    c[0] = d[3]; c[1] = d[2]; c[2] = d[1]; c[3] = d[0];
+    // p(t) = f0 + g0h t + t^2 s(t): s is the cubic Hermite interpolant of
+    // S = (p - f0 - g0h t) / t^2 and its derivative D at ta and tb, written in
+    // Newton's divided differences and expanded to monomials.  Three independent
+    // reciprocals instead of the four dependent pivots of a 4x4 elimination.
+    const double ta = x1 * ih, tb = x2 * ih;
+    const double ita = 1.0 / ta, itb = 1.0 / tb, iw = 1.0 / (tb - ta);
+    const double ita2 = ita * ita, itb2 = itb * itb;
+    const double Sa = (f1 - f0 - g0h * ta) * ita2;
+    const double Sb = (f2 - f0 - g0h * tb) * itb2;
+    const double Da = ((g1 - g0) * h - 2.0 * ta * Sa) * ita2;
+    const double Db = ((g2 - g0) * h - 2.0 * tb * Sb) * itb2;
+    const double m = (Sb - Sa) * iw;
+    const double e2 = (m - Da) * iw;
+    const double e3 = ((Db - m) - (m - Da)) * iw * iw;
+    c[0] = e3;
+    c[1] = e2 - e3 * (2.0 * ta + tb);
+    c[2] = Da + ta * (e3 * (ta + 2.0 * tb) - 2.0 * e2);
+    c[3] = Sa + ta * (ta * (e2 - e3 * tb) - Da);
     c[4] = g0h;
     c[5] = f0;
     nc = 6;
