@@ -273,6 +273,7 @@ __device__ __forceinline__ bool lm_step(const WarpCtx& C, double radius, const D
       break;
     }
     const double rs = rsqrt(sjj);
+    __syncwarp();  // every lane's reads of column j / row j are done before the column is overwritten
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int i = j + C.lane + 32 * p;
@@ -503,7 +504,9 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
       const double v = a[2 * l + (i & 1)] - (b ? b[2 * l + (i & 1)] : 0.0);
       acc += v * v;
     }
-    return sqrt(warp_sum(acc));
+    const double r = sqrt(warp_sum(acc));
+    __syncwarp();  // reads above are ordered before later writes of x (shuffles are not a memory barrier)
+    return r;
   };
   double x_norm = free_norm(C.x, nullptr);
 

@@ -529,6 +529,7 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
       b += dv * dv;
     }
     warp_sum2(a, b);
+    __syncwarp();  // the reads of x above are ordered before the accept step's writes (the shuffles are not a memory barrier)
     *xn2 = a;
     *dn2 = b;
   };

@@ -113,6 +113,17 @@ def test_duplicate_pairs_take_the_serial_assembly_path(b200, oracle):
     assert np.array_equal(st_g["iterations"], st_o["iterations"])
 
 
+@pytest.mark.parametrize("env,cfg", [("LFR_FORCE_V1", "cfg1"), ("LFR_FORCE_V1", "cfg3"), ("LFR_NO_TILE", "cfg4")])
+def test_fallback_tiers_match_oracle(b200, oracle, monkeypatch, env, cfg):
+    """The shared-memory Cholesky warp kernel (solve_warp_kernel) is the tier for
+    80 < n <= 96 unknowns and the fallback behind the register kernels; the
+    schedule reads LFR_FORCE_V1 / LFR_NO_TILE per plan, so the same scenes can be
+    sent through it (cfg4 without the tile tier: v1 for 32 < n <= 96)."""
+    monkeypatch.setenv(env, "1")
+    _, p = get_problem(cfg)
+    _compare(b200, oracle, p)
+
+
 def test_cta_pcg_tier_on_large_components(b200, oracle):
     """Components with more than 96 unknowns (ring scene, up to 60 nodes) take the
     CTA tier: matrix-free block-Jacobi PCG to 1e-13 stands in for the exact solve."""
