@@ -168,6 +168,44 @@ def test_quintic_interpolation_and_roots(oracle):
     np.testing.assert_allclose(out[:4], [0.1, 0.35, 0.36, 0.9], rtol=1e-10)
 
 
+def test_interpolant_minimiser_random_samples(oracle):
+    """Property test over random line-search states in Ceres' contraction range
+    (current step in [1e-3, 0.6] x previous, bracket [1e-3, 0.6] x current): the
+    returned minimiser is a global minimiser over the bracket of the degree-3 /
+    degree-5 Hermite interpolant built independently with numpy (Vandermonde solve
+    in x, polynomial.cc FindInterpolatingPolynomial), up to the conditioning of that
+    solve."""
+    rng = np.random.default_rng(1234)
+    for trial in range(400):
+        three = trial % 2 == 1
+        x2 = 10.0 ** rng.uniform(-3, 0)                     # previous step
+        x1 = x2 * (rng.uniform(0.02, 0.6) if three else 1.0)  # current step
+        f0, g0 = rng.normal(), -abs(rng.normal())           # descent direction at 0
+        f1, g1, f2, g2 = rng.normal(size=4) * np.array([1.0, 3.0 / x1, 1.0, 3.0 / x2])
+        s = [[0.0, f0, g0, 1, 1], [x1, f1, g1, 1, 1]] + ([[x2, f2, g2, 1, 1]] if three else [])
+        lo, hi = 1e-3 * x1, 0.6 * x1
+        x, v = minimize_interp(oracle, s, lo, hi)
+        # independent construction, normalised abscissae for conditioning
+        h = max(r[0] for r in s)
+        rows, rhs = [], []
+        deg = 2 * len(s) - 1
+        for (xs, fs, gs, _, _) in s:
+            t = xs / h
+            rows.append([t ** k for k in range(deg, -1, -1)])
+            rhs.append(fs)
+            rows.append([k * t ** (k - 1) if k > 0 else 0.0 for k in range(deg, -1, -1)])
+            rhs.append(gs * h)
+        co = np.linalg.solve(np.array(rows), np.array(rhs))
+        p = np.poly1d(co)
+        cand = [lo / h, hi / h, 0.5 * (lo + hi) / h] + [r.real for r in p.deriv().roots
+                                                       if abs(r.imag) < 1e-9 and lo / h <= r.real <= hi / h]
+        best = min(p(c) for c in cand)
+        scale = max(1.0, np.abs(co).max())
+        assert lo <= x <= hi
+        assert abs(v - p(x / h)) <= 1e-9 * scale, (trial, v, p(x / h))
+        assert v <= best + 1e-9 * scale, (trial, v, best)
+
+
 def _two_node_problem(t, sim=0.9):
     """One match between two images, constant flows d12 = t, d21 = -t."""
     from lfr_b200 import MatchSet, build_problem
