@@ -43,7 +43,7 @@ struct Warp2Layout {
     scr = o; o += 8 * 7 * emax;
     tup = o; o += 8 * 5 * emax;
     o = align_up(o, 16);
-    prow = o; o += 8 * 2 * 36;  // double-buffered pivot row of the elimination (32 columns, rhs, 1/pivot, pivot)
+    prow = o; o += 8 * 2 * 72;  // double-buffered pivot rows of the elimination: 2 rows x (32 columns, rhs, spare)
     eidx = o; o += 4 * emax;
     meta = o; o += 4 * emax;
     node = o; o += 4 * ncmax;
@@ -244,6 +244,13 @@ __device__ __forceinline__ double assemble2(const Warp2Ctx& C, bool first, const
 // (S H S + D^2) y = S g by Gauss-Jordan elimination with the rows in registers
 // (lane i <-> row i, n <= NREG <= 32).  Writes dl = -S y; returns validity and
 // {model_cost_change, g . dl, |dl|_inf}.
+// NREG up to which lm_step2 eliminates with 2x2 block pivots (above: scalar pivots;
+// two published rows plus the register row would not fit in 255 registers)
+#ifndef LFR_BLOCK_PIVOT_MAX_NREG
+#define LFR_BLOCK_PIVOT_MAX_NREG 24
+#endif
+constexpr int kBlockPivotMaxNreg = LFR_BLOCK_PIVOT_MAX_NREG;
+
 template <int NREG>
 __device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const DevConsts& K,
                                          double* model_change, double* gd, double* dmax) {
@@ -275,6 +282,51 @@ __device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const
   // No per-element guards: all NREG slots are processed every step (slots past
   // the live columns hold zeros), so the step is a straight run of 128-bit
   // shared-memory accesses and DFMAs that the scheduler can overlap freely.
+  double y;
+  if constexpr (NREG <= kBlockPivotMaxNreg) {
+    // 2x2 block pivots (n = 2 x free nodes is even; the diagonal blocks of an SPD
+    // matrix are SPD): half as many publish / synchronise / reciprocal rounds on
+    // the dependent chain for the same number of DFMAs.  Lanes j, j+1 publish
+    // their raw rows; every lane inverts the 2x2 pivot block B itself.
+    constexpr int R = NREG + 2;  // second published row (16-byte aligned: NREG is even)
+    double inv0 = 0.0, inv1 = 0.0;  // this lane's row of B^-1 (pivot lanes)
+    for (int j = 0; j < n; j += 2) {
+      double* buf = C.prow + ((j >> 1) & 1) * C.prow_stride;
+      if (i == j || i == j + 1) {
+        double* row = buf + (i - j) * R;
+        double2* row2 = reinterpret_cast<double2*>(row);
+#pragma unroll
+        for (int k = 0; k < NREG; k += 2) row2[k / 2] = make_double2(a[k], a[k + 1]);
+        row[NREG] = b;
+      }
+      __syncwarp();
+      const double2* r0 = reinterpret_cast<const double2*>(buf);
+      const double2* r1 = reinterpret_cast<const double2*>(buf + R);
+      const double2 p0 = r0[0], p1 = r1[0];  // B = [p0.x p0.y; p1.x p1.y]
+      const double bj0 = buf[NREG], bj1 = buf[R + NREG];
+      const double det = p0.x * p1.y - p0.y * p1.x;
+      ok = ok && (p0.x > 0.0) && (det > 0.0) && isfinite(det);
+      const double rdet = 1.0 / det;
+      const bool piv_lane = (i == j) || (i == j + 1);
+      if (i == j) { inv0 = p1.y * rdet; inv1 = -p0.y * rdet; }
+      if (i == j + 1) { inv0 = -p1.x * rdet; inv1 = p0.x * rdet; }
+      // [f0 f1] B = [a0 a1]; the pivot rows themselves are kept (raw)
+      const double f0 = piv_lane ? 0.0 : (a[0] * p1.y - a[1] * p1.x) * rdet;
+      const double f1 = piv_lane ? 0.0 : (a[1] * p0.x - a[0] * p0.y) * rdet;
+#pragma unroll
+      for (int k = 2; k < NREG; k += 2) {
+        const double2 u = r0[k / 2], v = r1[k / 2];
+        a[k - 2] = a[k] - f0 * u.x - f1 * v.x;
+        a[k - 1] = a[k + 1] - f0 * u.y - f1 * v.y;
+      }
+      a[NREG - 2] = 0.0;
+      a[NREG - 1] = 0.0;
+      b -= f0 * bj0 + f1 * bj1;
+    }
+    // rows j, j+1 now read  B [y_j y_j+1]^T = [b_j b_j+1]^T
+    const double bp = __shfl_xor_sync(kFull, b, 1);
+    y = (i & 1) ? inv0 * bp + inv1 * b : inv0 * b + inv1 * bp;
+  } else {
   double myrp = 1.0;
   for (int j = 0; j < n; ++j) {
     double* buf = C.prow + (j & 1) * C.prow_stride;
@@ -299,7 +351,8 @@ __device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const
     a[NREG - 1] = 0.0;
     b -= f * bj;
   }
-  const double y = b * myrp;  // row i now reads  piv_i * y_i = b_i
+  y = b * myrp;  // row i now reads  piv_i * y_i = b_i
+  }
   double mc = 0.0, dot = 0.0, mx = 0.0;
   bool finite = true;
   if (act) {
@@ -466,7 +519,7 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   C.scr = (double*)(base + L.scr);
   C.tup = (double*)(base + L.tup);
   C.prow = (double*)(base + L.prow);
-  C.prow_stride = 36;
+  C.prow_stride = 72;
   C.eidx = (uint32_t*)(base + L.eidx);
   C.meta = (uint32_t*)(base + L.meta);
   C.node = (uint32_t*)(base + L.node);
