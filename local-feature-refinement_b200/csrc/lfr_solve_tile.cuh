@@ -28,7 +28,7 @@ struct TileLayout {
     scr = o; o += 8 * 7 * emax;
     tup = o; o += 8 * 5 * emax;
     o = align_up(o, 16);
-    prow = o; o += 8 * 2 * 84;   // double-buffered pivot row: 80 columns, rhs, spare
+    prow = o; o += 8 * 4 * 84;   // double-buffered pair of pivot rows: 2 x 2 x (80 columns, rhs, spare)
     red = o; o += 8 * 3 * 4;     // block reductions (<= 4 warps)
     hdr = o; o += 16;            // Ec, nf, irregular broadcast by warp 0
     eidx = o; o += 4 * emax;
@@ -262,38 +262,57 @@ __device__ __forceinline__ bool tile_lm_step(const TileCtx<T>& C, double radius,
     a[k] = v;
   }
   const double b0 = si * gi;
-  double b = b0, myrp = 1.0;
+  double b = b0;
   bool ok = true;
-  for (int j = 0; j < n; ++j) {
-    double* buf = C.prow + (j & 1) * 84;
-    double2* buf2 = reinterpret_cast<double2*>(buf);
-    if (i == j) {
+  // 2x2 block pivots (see lm_step2 in lfr_solve_warp2.cuh): threads j, j+1 publish
+  // their raw rows, every thread inverts the pivot block itself; half as many
+  // block-wide barriers as scalar pivots.
+  constexpr int R = 84;
+  double inv0 = 0.0, inv1 = 0.0;
+  for (int j = 0; j < n; j += 2) {
+    double* buf = C.prow + ((j >> 1) & 1) * (2 * R);
+    if (i == j || i == j + 1) {
+      double* row = buf + (i - j) * R;
+      double2* row2 = reinterpret_cast<double2*>(row);
 #pragma unroll
-      for (int k = 0; k < NREG; k += 2) buf2[k / 2] = make_double2(a[k], a[k + 1]);
-      buf[NREG] = b;
+      for (int k = 0; k < NREG; k += 2) row2[k / 2] = make_double2(a[k], a[k + 1]);
+      row[NREG] = b;
     }
     __syncthreads();
-    const double piv = buf[0];
-    const double bj = buf[NREG];
-    ok = ok && (piv > 0.0) && isfinite(piv);
-    const double rp = 1.0 / piv;
-    if (i == j) myrp = rp;
-    const double f = (i == j) ? 0.0 : a[0] * rp;
+    const double2* r0 = reinterpret_cast<const double2*>(buf);
+    const double2* r1 = reinterpret_cast<const double2*>(buf + R);
+    const double2 p0 = r0[0], p1 = r1[0];
+    const double bj0 = buf[NREG], bj1 = buf[R + NREG];
+    const double det = p0.x * p1.y - p0.y * p1.x;
+    ok = ok && (p0.x > 0.0) && (det > 0.0) && isfinite(det);
+    const double rdet = 1.0 / det;
+    const bool piv_thread = (i == j) || (i == j + 1);
+    if (i == j) { inv0 = p1.y * rdet; inv1 = -p0.y * rdet; }
+    if (i == j + 1) { inv0 = -p1.x * rdet; inv1 = p0.x * rdet; }
+    const double f0 = piv_thread ? 0.0 : (a[0] * p1.y - a[1] * p1.x) * rdet;
+    const double f1 = piv_thread ? 0.0 : (a[1] * p0.x - a[0] * p0.y) * rdet;
 #pragma unroll
-    for (int k0 = 0; k0 < NREG; k0 += 8) {  // loads in groups of four 128-bit words
-      double2 t[4];
+    for (int k0 = 2; k0 < NREG; k0 += 4) {  // two 128-bit words of each row per group
+      double2 u[2], v[2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) t[q] = buf2[k0 / 2 + q];
+      for (int q = 0; q < 2; ++q) {
+        if (k0 + 2 * q < NREG) { u[q] = r0[k0 / 2 + q]; v[q] = r1[k0 / 2 + q]; }
+      }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int k = k0 + q;
-        if (k >= 1) a[k - 1] = a[k] - f * ((q & 1) ? t[q / 2].y : t[q / 2].x);
+      for (int q = 0; q < 2; ++q) {
+        const int k = k0 + 2 * q;
+        if (k < NREG) {
+          a[k - 2] = a[k] - f0 * u[q].x - f1 * v[q].x;
+          a[k - 1] = a[k + 1] - f0 * u[q].y - f1 * v[q].y;
+        }
       }
     }
+    a[NREG - 2] = 0.0;
     a[NREG - 1] = 0.0;
-    b -= f * bj;
+    b -= f0 * bj0 + f1 * bj1;
   }
-  const double y = b * myrp;
+  const double bp = __shfl_xor_sync(0xffffffffu, b, 1);
+  const double y = (i & 1) ? inv0 * bp + inv1 * b : inv0 * b + inv1 * bp;
   double mc = 0.0, dot = 0.0, bad = 0.0, mx = 0.0;
   if (act) {
     const double d = -si * y;

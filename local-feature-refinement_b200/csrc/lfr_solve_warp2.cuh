@@ -244,10 +244,10 @@ __device__ __forceinline__ double assemble2(const Warp2Ctx& C, bool first, const
 // (S H S + D^2) y = S g by Gauss-Jordan elimination with the rows in registers
 // (lane i <-> row i, n <= NREG <= 32).  Writes dl = -S y; returns validity and
 // {model_cost_change, g . dl, |dl|_inf}.
-// NREG up to which lm_step2 eliminates with 2x2 block pivots (above: scalar pivots;
-// two published rows plus the register row would not fit in 255 registers)
+// NREG up to which lm_step2 eliminates with 2x2 block pivots (above: scalar pivots,
+// kept for comparison; -DLFR_BLOCK_PIVOT_MAX_NREG=0 restores them everywhere)
 #ifndef LFR_BLOCK_PIVOT_MAX_NREG
-#define LFR_BLOCK_PIVOT_MAX_NREG 24
+#define LFR_BLOCK_PIVOT_MAX_NREG 32
 #endif
 constexpr int kBlockPivotMaxNreg = LFR_BLOCK_PIVOT_MAX_NREG;
 
