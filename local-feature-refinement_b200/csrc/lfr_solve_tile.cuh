@@ -95,8 +95,10 @@ __device__ __forceinline__ double tile_max(const TileCtx<T>& C, double v) {
   return v;
 }
 
-template <int T>
-__device__ __forceinline__ double tile_eval(const TileCtx<T>& C, const double* xe, const DevConsts& K) {
+// DIRDERIV: also grad f(xe) . dl, per edge from the same evaluation (see eval_pass2)
+template <int T, bool DIRDERIV>
+__device__ __forceinline__ double tile_eval(const TileCtx<T>& C, const double* xe, const DevConsts& K,
+                                            double* dphi = nullptr) {
   double cost = 0.0, z1 = 0.0, z2 = 0.0;
   for (int j = C.tid; j < C.Ec; j += T) {
     const uint32_t mt = C.meta[j];
@@ -115,8 +117,15 @@ __device__ __forceinline__ double tile_eval(const TileCtx<T>& C, const double* x
     sc[5 * C.emax] = ev.m10;
     sc[6 * C.emax] = ev.m11;
     cost += ev.half_rho;
+    if (DIRDERIV) {
+      const int fs = C.freeof[s], fd = C.freeof[d];
+      const double s0 = fs >= 0 ? C.dl[2 * fs] : 0.0, s1 = fs >= 0 ? C.dl[2 * fs + 1] : 0.0;
+      const double d0 = fd >= 0 ? C.dl[2 * fd] : 0.0, d1 = fd >= 0 ? C.dl[2 * fd + 1] : 0.0;
+      z1 += ev.a * (ev.r0 * (d0 - (ev.m00 * s0 + ev.m01 * s1)) + ev.r1 * (d1 - (ev.m10 * s0 + ev.m11 * s1)));
+    }
   }
   tile_sum3(C, cost, z1, z2);  // (its barriers also publish the staged values)
+  if (DIRDERIV) *dphi = z1;
   return cost;
 }
 
@@ -406,7 +415,7 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     return;
   }
 
-  double cost = tile_eval(C, C.x, K);
+  double cost = tile_eval<T, false>(C, C.x, K);
   double gmax = tile_assemble<T, false>(C, true, K);
   const double cost0 = cost;
   double radius = K.radius0, nu = 2.0;
@@ -441,7 +450,7 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     }
     n_invalid = 0;
     tile_candidate(C, 1.0, K);
-    double cost_c = tile_eval(C, C.xc, K);
+    double cost_c = tile_eval<T, false>(C, C.xc, K);
     bool c_valid = isfinite(cost_c);
     if (!c_valid || cost_c > cost + K.ls_suff * gd * 1.0) {
       LsSample initial{0.0, cost, gd, true, true};
@@ -461,12 +470,13 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
         if (step * dmax < K.ls_min_step) break;
         previous = current;
         tile_candidate(C, step, K);
-        cost_c = tile_eval(C, C.xc, K);
+        double dphi;
+        cost_c = tile_eval<T, true>(C, C.xc, K, &dphi);
         c_valid = isfinite(cost_c);
         current = LsSample{step, cost_c, 0.0, c_valid, false};
         if (c_valid) {
-          current.gradient = tile_assemble<T, true>(C, false, K);
-          current.gradient_valid = isfinite(current.gradient);
+          current.gradient = dphi;
+          current.gradient_valid = isfinite(dphi);
         }
         if (c_valid && !(cost_c > cost + K.ls_suff * gd * step)) { ls_ok = true; break; }
       }
@@ -475,7 +485,7 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
         __syncthreads();
       } else {
         tile_candidate(C, 1.0, K);
-        cost_c = tile_eval(C, C.xc, K);
+        cost_c = tile_eval<T, false>(C, C.xc, K);
         c_valid = isfinite(cost_c);
       }
     }

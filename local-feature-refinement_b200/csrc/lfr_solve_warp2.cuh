@@ -89,8 +89,14 @@ __device__ __forceinline__ void warp_sum2(double& s0, double& s1) {
 }
 
 // Same staging as eval_pass (lfr_solve_warp.cuh) for the v2 context.
-__device__ __forceinline__ double eval_pass2(const Warp2Ctx& C, const double* xe, const DevConsts& K) {
-  double cost = 0.0;
+// DIRDERIV = true additionally returns phi'(alpha) = grad f(xe) . dl of the line
+// search, accumulated per edge from the same evaluation:
+//   grad . dl = sum_e a_e r_e^T (dl_dst - M_e dl_src)      (J_src = -M, J_dst = I)
+// so a line-search trial needs no separate gradient assembly pass.
+template <bool DIRDERIV>
+__device__ __forceinline__ double eval_pass2(const Warp2Ctx& C, const double* xe, const DevConsts& K,
+                                             double* dphi = nullptr) {
+  double cost = 0.0, dd = 0.0;
   for (int j = C.lane; j < C.Ec; j += 32) {
     const uint32_t mt = C.meta[j];
     const int s = mt & 0xfff, d = (mt >> 12) & 0xfff, kind = mt >> 24;
@@ -108,8 +114,19 @@ __device__ __forceinline__ double eval_pass2(const Warp2Ctx& C, const double* xe
     sc[5 * C.emax] = ev.m10;
     sc[6 * C.emax] = ev.m11;
     cost += ev.half_rho;
+    if (DIRDERIV) {
+      const int fs = C.freeof[s], fd = C.freeof[d];
+      const double s0 = fs >= 0 ? C.dl[2 * fs] : 0.0, s1 = fs >= 0 ? C.dl[2 * fs + 1] : 0.0;
+      const double d0 = fd >= 0 ? C.dl[2 * fd] : 0.0, d1 = fd >= 0 ? C.dl[2 * fd + 1] : 0.0;
+      dd += ev.a * (ev.r0 * (d0 - (ev.m00 * s0 + ev.m01 * s1)) + ev.r1 * (d1 - (ev.m10 * s0 + ev.m11 * s1)));
+    }
   }
-  cost = warp_sum(cost);
+  if (DIRDERIV) {
+    warp_sum2(cost, dd);
+    *dphi = dd;
+  } else {
+    cost = warp_sum(cost);
+  }
   __syncwarp();
   return cost;
 }
@@ -563,7 +580,7 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   LFR_TICK(cyc_setup);
 
   // ---- iteration 0 -----------------------------------------------------------------
-  double cost = eval_pass2(C, C.x, K);
+  double cost = eval_pass2<false>(C, C.x, K);
   LFR_TICK(cyc_eval);
   double gmax = assemble2<false>(C, true, K);
   LFR_TICK(cyc_asm);
@@ -618,7 +635,7 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     n_invalid = 0;
     // projected Armijo line search along dl (bounds-constrained problem, A.7b)
     make_candidate2(C, 1.0, K);
-    double cost_c = eval_pass2(C, C.xc, K);
+    double cost_c = eval_pass2<false>(C, C.xc, K);
     LFR_TICK(cyc_eval);
     bool c_valid = isfinite(cost_c);
     if (!c_valid || cost_c > cost + K.ls_suff * gd * 1.0) {
@@ -641,12 +658,13 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
         if (step * dmax < K.ls_min_step) break;
         previous = current;
         make_candidate2(C, step, K);
-        cost_c = eval_pass2(C, C.xc, K);
+        double dphi;
+        cost_c = eval_pass2<true>(C, C.xc, K, &dphi);
         c_valid = isfinite(cost_c);
         current = LsSample{step, cost_c, 0.0, c_valid, false};
         if (c_valid) {
-          current.gradient = assemble2<true>(C, false, K);
-          current.gradient_valid = isfinite(current.gradient);
+          current.gradient = dphi;
+          current.gradient_valid = isfinite(dphi);
         }
         if (c_valid && !(cost_c > cost + K.ls_suff * gd * step)) { ls_ok = true; break; }
       }
@@ -655,7 +673,7 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
         __syncwarp();
       } else {  // line search failed: delta unchanged, candidate = P(x + delta)
         make_candidate2(C, 1.0, K);
-        cost_c = eval_pass2(C, C.xc, K);
+        cost_c = eval_pass2<false>(C, C.xc, K);
         c_valid = isfinite(cost_c);
       }
     }
