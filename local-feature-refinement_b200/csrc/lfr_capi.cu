@@ -830,4 +830,31 @@ int lfr_debug_edge_eval(const lfr_edge* edges, const uint8_t* kind, uint64_t n, 
   return rc;
 }
 
+/* test hook: real roots in [lo, hi] of n quartics (5 coefficients each, highest degree first,
+   leading coefficient != 0) by the line search's root finders; use_grid = 1 -> Budan-Fourier grid
+   isolation (the production route), 0 -> derivative recursion */
+int lfr_debug_quartic_roots(const double* coef, const double* lohi, uint64_t n, int use_grid, double* roots,
+                            int* counts) {
+  lfr_options o;
+  lfr_options_default(&o);
+  LFR_TRY(select_device(o));
+  if (n == 0) return LFR_OK;
+  DevBuf d_c, d_l, d_r, d_n;
+  auto run = [&]() -> int {
+    LFR_TRY(upload(&d_c, coef, 5 * n, 0));
+    LFR_TRY(upload(&d_l, lohi, 2 * n, 0));
+    LFR_TRY(d_r.reserve(n * 32));
+    LFR_TRY(d_n.reserve(n * 4));
+    lfr::quartic_roots_kernel<<<(unsigned)((n + 3) / 4), 128>>>(d_c.as<double>(), d_l.as<double>(), (int)n, use_grid,
+                                                                d_r.as<double>(), d_n.as<int>());
+    LFR_CUDA(cudaGetLastError());
+    LFR_CUDA(cudaMemcpy(roots, d_r.p, n * 32, cudaMemcpyDeviceToHost));
+    LFR_CUDA(cudaMemcpy(counts, d_n.p, n * 4, cudaMemcpyDeviceToHost));
+    return LFR_OK;
+  };
+  const int rc = run();
+  d_c.release(); d_l.release(); d_r.release(); d_n.release();
+  return rc;
+}
+
 }  // extern "C"

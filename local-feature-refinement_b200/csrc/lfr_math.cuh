@@ -270,7 +270,8 @@ __device__ __noinline__ int real_roots_in(const double* c, int n, double lo, dou
 #ifdef LFR_POLY_PROF
 // Diagnostic build only (-DLFR_POLY_PROF): cycle split of hermite_minimizer, read
 // back with lfr_debug_poly_prof().  [0] coefficients [1] first evaluations
-// [2] quadratic [3] cubic level [4] quartic level [5] final evaluations
+// [2] grid classification (or quadratic) [3] extremum cells (or cubic level)
+// [4] root solves (or quartic level) [5] final evaluations
 // [6] quintic calls [7] cubic calls [8] Newton iterations [9] bracket_root calls
 // [10] whole cubic-interpolant call
 __device__ unsigned long long g_poly_prof[16];
@@ -408,6 +409,99 @@ __device__ __forceinline__ int quartic_roots_in(const double (&q)[5], double lo,
   return n4;
 }
 
+// ---- Budan-Fourier grid isolation of the quartic's roots ----------------------
+// The derivative recursion above runs three dependent stages (quadratic, cubic,
+// quartic) with a handful of lanes.  Here all 32 lanes work at once: lane L takes
+// the grid point t_L = lo + L (hi - lo) / 31 and computes the Taylor coefficients
+// of q there (q, q', q"/2, q(3)/6, q(4)/24) by repeated synthetic division.
+// With V(t) = number of sign variations of that sequence, Budan-Fourier says the
+// number of roots of q in (t_L, t_L+1] is D = V(t_L) - V(t_L+1) minus an even
+// number.  So a cell with
+//   D = 0                 has no root,
+//   D = 1                 has exactly one (q changes sign across it),
+//   D = 2, D' = 0         has none   (D' = the same count for q': q is monotone),
+//   D = 2, D' = 1         has none or two: q has exactly one extremum e in the
+//                         cell (bracketed by the sign change of q'), and the sign
+//                         of q(e) decides; the two roots are then bracketed by
+//                         [t_L, e] and [e, t_L+1],
+//   D = 3, D' = 0         has exactly one (monotone),
+// and every other case (two extrema inside one cell, an exact zero on the grid,
+// non-finite values) goes to the derivative recursion, which stays the reference.
+// Every root is polished by the same safeguarded Newton as before, from a bracket
+// 31x tighter, so both routes return the same roots up to the last bits.
+__device__ __forceinline__ int quartic_roots_grid(const double (&q)[5], double lo, double hi, double (&out)[4],
+                                                  int lane, long long& pp_t) {
+  const double w = (hi - lo) * (1.0 / 31.0);
+  const double t = lane == 31 ? hi : fma(w, (double)lane, lo);
+  double a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
+  const double a0 = q[0];
+  a1 = fma(a0, t, a1); a2 = fma(a1, t, a2); a3 = fma(a2, t, a3); a4 = fma(a3, t, a4);  // a4 = q(t)
+  a1 = fma(a0, t, a1); a2 = fma(a1, t, a2); a3 = fma(a2, t, a3);                       // a3 = q'(t)
+  a1 = fma(a0, t, a1); a2 = fma(a1, t, a2);                                            // a2 = q"(t) / 2
+  a1 = fma(a0, t, a1);                                                                 // a1 = q(3)(t) / 6
+  const bool bad = !isfinite(a4) || a4 == 0.0 || a3 == 0.0 || a2 == 0.0 || a1 == 0.0;
+  const int n4 = a4 < 0.0, n3 = a3 < 0.0, n2 = a2 < 0.0, n1 = a1 < 0.0, n0 = a0 < 0.0;
+  const int Vp = (n3 ^ n2) + (n2 ^ n1) + (n1 ^ n0);
+  const int V = (n4 ^ n3) + Vp;
+  const int Vn = __shfl_down_sync(0xffffffffu, V, 1), Vpn = __shfl_down_sync(0xffffffffu, Vp, 1);
+  const double tn = __shfl_down_sync(0xffffffffu, t, 1);
+  const double qn = __shfl_down_sync(0xffffffffu, a4, 1), dqn = __shfl_down_sync(0xffffffffu, a3, 1);
+  int kind = 0;  // 0 no root, 1 one root in [t, tn], 2 one extremum to examine, 3 undecided
+  if (lane < 31) {
+    const int D = V - Vn, Dp = Vp - Vpn;
+    if (D < 0 || Dp < 0 || D > 3) kind = 3;
+    else if (D == 1) kind = 1;
+    else if (D == 2) kind = Dp == 0 ? 0 : (Dp == 1 ? 2 : 3);
+    else if (D == 3) kind = Dp == 0 ? 1 : 3;
+  }
+  if (__any_sync(0xffffffffu, bad || kind == 3)) return quartic_roots_in(q, lo, hi, out, lane, pp_t);
+  LFR_PP_TICK(2);
+  // cells with one extremum of q: find it, look at the sign of q there
+  int nl = kind == 1 ? 1 : 0;
+  double xb = tn, fb = qn, e = 0.0, qe = 0.0;
+  if (__any_sync(0xffffffffu, kind == 2)) {
+    if (kind == 2) {
+      const double d3[4] = {4.0 * q[0], 3.0 * q[1], 2.0 * q[2], q[3]};
+      e = bracket_root_n<4>(d3, t, tn, a3, dqn);
+      qe = poly_eval_n<5>(q, e);
+      if (qe != 0.0 && ((qe < 0.0) != (a4 < 0.0))) {  // q crosses zero on both sides of e
+        nl = 2;
+        xb = e;
+        fb = qe;
+      }
+    }
+  }
+  LFR_PP_TICK(3);
+  double ra = 0.0, rb = 0.0;
+  if (nl >= 1) ra = bracket_root_n<5>(q, t, xb, a4, fb);
+  if (__any_sync(0xffffffffu, nl == 2)) {
+    if (nl == 2) rb = bracket_root_n<5>(q, e, tn, qe, qn);
+  }
+  // gather in ascending order (cells are ordered, ra < rb inside a cell)
+  unsigned m1 = __ballot_sync(0xffffffffu, nl >= 1);
+  const unsigned m2 = __ballot_sync(0xffffffffu, nl == 2);
+  int cnt = 0;
+  double last = 0.0;
+  while (m1) {
+    const int L = __ffs(m1) - 1;
+    m1 &= m1 - 1;
+    const double r1 = __shfl_sync(0xffffffffu, ra, L), r2 = __shfl_sync(0xffffffffu, rb, L);
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const double r = rep == 0 ? r1 : r2;
+      if ((rep == 0 || ((m2 >> L) & 1u)) && cnt < 4 && (cnt == 0 || r != last)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (cnt == k) out[k] = r;
+        last = r;
+        ++cnt;
+      }
+    }
+  }
+  LFR_PP_TICK(4);
+  return cnt;
+}
+
 // Minimiser over [lo, hi] (in x) of the Hermite interpolant through (0, f0, g0),
 // (x1, f1, g1) [and (x2, f2, g2) if three == true].  Warp-uniform.
 __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1, double f1, double g1,
@@ -468,7 +562,11 @@ __device__ __noinline__ double hermite_minimizer(double f0, double g0, double x1
     const double der4[5] = {5.0 * c6[0], 4.0 * c6[1], 3.0 * c6[2], 2.0 * c6[3], c6[4]};
     double roots[4] = {0.0, 0.0, 0.0, 0.0};
     LFR_PP_TICK(1);
+#ifdef LFR_NO_GRID_ROOTS
     const int nr = quartic_roots_in(der4, tlo, thi, roots, lane, pp_t);
+#else
+    const int nr = quartic_roots_grid(der4, tlo, thi, roots, lane, pp_t);
+#endif
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (i < nr && roots[i] >= tlo && roots[i] <= thi) {

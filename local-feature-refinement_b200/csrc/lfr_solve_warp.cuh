@@ -636,6 +636,23 @@ __global__ void local_index_kernel(const uint32_t* comp_ptr, const uint32_t* com
   local_of[comp_nodes[i]] = i - comp_ptr[lo];
 }
 
+// Test hook: the line search's quartic root finders on caller-supplied polynomials,
+// one warp per polynomial (lfr_debug_quartic_roots).
+__global__ void quartic_roots_kernel(const double* __restrict__ coef, const double* __restrict__ lohi, int n,
+                                     int use_grid, double* __restrict__ roots, int* __restrict__ counts) {
+  const int wid = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (wid >= n) return;  // whole warps leave together
+  const double q[5] = {coef[5 * wid], coef[5 * wid + 1], coef[5 * wid + 2], coef[5 * wid + 3], coef[5 * wid + 4]};
+  double out[4] = {0.0, 0.0, 0.0, 0.0};
+  long long pp = 0;
+  const int c = use_grid ? quartic_roots_grid(q, lohi[2 * wid], lohi[2 * wid + 1], out, lane, pp)
+                         : quartic_roots_in(q, lohi[2 * wid], lohi[2 * wid + 1], out, lane, pp);
+  if (lane == 0) {
+    counts[wid] = c;
+    for (int k = 0; k < 4; ++k) roots[4 * wid + k] = out[k];
+  }
+}
+
 // K1 test hook: one thread per edge.
 __global__ void edge_eval_kernel(const float4* edges, const uint8_t* kind, uint64_t n, const double* xs,
                                  const double* xd, const DevConsts K, double* r, double* jac, double* rho) {

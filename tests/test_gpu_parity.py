@@ -124,6 +124,90 @@ def test_fallback_tiers_match_oracle(b200, oracle, monkeypatch, env, cfg):
     _compare(b200, oracle, p)
 
 
+def _quartic_cases(rng, n):
+    """Quartics in the shapes the line search produces (derivative of a quintic
+    interpolant on [1e-3, 0.6] x step) plus adversarial ones: complex pairs whose
+    real part lies inside the interval, close root pairs, roots near the 31-cell grid."""
+    coef, lohi = [], []
+    for k in range(n):
+        mode = k % 6
+        if mode == 0:      # four real roots, anywhere
+            r = rng.uniform(-0.5, 1.5, size=4)
+            q = np.poly(r)
+        elif mode == 1:    # two real + complex pair with its real part inside the interval
+            a, b = rng.uniform(0.05, 0.55), 10.0 ** rng.uniform(-4, 0)
+            q = np.real(np.poly([rng.uniform(-0.5, 1.5), rng.uniform(-0.5, 1.5), a + 1j * b, a - 1j * b]))
+        elif mode == 2:    # two complex pairs
+            a1, b1 = rng.uniform(0.0, 0.6), 10.0 ** rng.uniform(-3, 0)
+            a2, b2 = rng.uniform(0.0, 0.6), 10.0 ** rng.uniform(-3, 0)
+            q = np.real(np.poly([a1 + 1j * b1, a1 - 1j * b1, a2 + 1j * b2, a2 - 1j * b2]))
+        elif mode == 3:    # a close pair (separation 1e-2 .. 1e-5) inside the interval
+            c, sep = rng.uniform(0.05, 0.55), 10.0 ** rng.uniform(-5, -2)
+            q = np.poly([c - sep / 2, c + sep / 2, rng.uniform(-0.5, 1.5), rng.uniform(-0.5, 1.5)])
+        elif mode == 4:    # a root within 1e-9 of a grid point
+            g = 1e-3 + (0.6 - 1e-3) * rng.integers(1, 30) / 31.0
+            q = np.poly([g * (1 + rng.uniform(-1e-9, 1e-9)), rng.uniform(0, 0.6), rng.uniform(-1, 2), rng.uniform(-1, 2)])
+        else:              # random coefficients
+            q = rng.normal(size=5)
+        q = q * (10.0 ** rng.uniform(-3, 3)) * rng.choice([-1.0, 1.0])
+        coef.append(q)
+        lohi.append([1e-3, 0.6] if k % 2 == 0 else sorted(rng.uniform(-0.2, 1.2, size=2)))
+    return np.ascontiguousarray(coef, dtype=np.float64), np.ascontiguousarray(lohi, dtype=np.float64)
+
+
+def test_quartic_root_finders_agree(b200, oracle):
+    """The line search's Budan-Fourier grid isolation (production) against the
+    derivative recursion on the GPU and in the oracle (lfr_ref_polynomial_roots):
+    same number of roots, every one a root to working precision (backward error
+    <= 1e-12) and at the same place up to the conditioning of root clusters (1e-6);
+    a pair of roots closer than 1e-6 (a near-double root, irrelevant to the
+    minimisation) may be found by one route and not the other."""
+    import ctypes as C
+    rng = np.random.default_rng(99)
+    n = 6000
+    coef, lohi = _quartic_cases(rng, n)
+    f = b200.lib.lfr_debug_quartic_roots
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    res = {}
+    for use_grid in (0, 1):
+        roots = np.zeros((n, 4))
+        cnt = np.zeros(n, dtype=np.int32)
+        assert f(coef.ctypes.data, lohi.ctypes.data, n, use_grid, roots.ctypes.data, cnt.ctypes.data) == 0
+        res[use_grid] = (roots, cnt)
+    ro = np.zeros((n, 8))
+    co = np.zeros(n, dtype=np.int32)
+    for k in range(n):
+        co[k] = oracle.lib.lfr_ref_polynomial_roots(coef[k].ctypes.data, 5, float(lohi[k, 0]), float(lohi[k, 1]),
+                                                    ro[k].ctypes.data)
+
+    def same(k, ra, na, rb, nb):
+        a, b = list(ra[:na]), list(rb[:nb])
+        # every returned value is a root to working precision (backward error), whatever the
+        # conditioning of a root cluster does to its position
+        for r in a:
+            mag = np.polyval(np.abs(coef[k]), abs(r))
+            if abs(np.polyval(coef[k], r)) > 1e-12 * mag:
+                return False
+        if na == nb:
+            return np.allclose(a, b, rtol=1e-6, atol=1e-9)
+        # tolerate a missing near-double pair
+        long_, short = (a, b) if na > nb else (b, a)
+        if len(long_) - len(short) != 2:
+            return False
+        for i in range(len(long_) - 1):
+            if abs(long_[i + 1] - long_[i]) <= 1e-6 * max(1.0, abs(long_[i])):
+                rest = long_[:i] + long_[i + 2:]
+                if np.allclose(rest, short, rtol=1e-6, atol=1e-9):
+                    return True
+        return False
+
+    bad = [k for k in range(n) if not same(k, res[1][0][k], res[1][1][k], ro[k], co[k])]
+    assert not bad, (len(bad), bad[:5], [(res[1][0][k][:res[1][1][k]], ro[k][:co[k]]) for k in bad[:3]])
+    bad0 = [k for k in range(n) if not same(k, res[0][0][k], res[0][1][k], ro[k], co[k])]
+    assert not bad0, (len(bad0), bad0[:5])
+    assert (res[1][1] > 0).mean() > 0.4 and (res[1][1] >= 3).sum() > 100   # the cases do exercise multi-root cells
+
+
 def test_cta_pcg_tier_on_large_components(b200, oracle):
     """Components with more than 96 unknowns (ring scene, up to 60 nodes) take the
     CTA tier: matrix-free block-Jacobi PCG to 1e-13 stands in for the exact solve."""

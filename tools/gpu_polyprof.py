@@ -25,7 +25,7 @@ lib.lib.lfr_debug_poly_prof(out.ctypes.data, 1)
 plan.solve()
 torch.cuda.synchronize()
 lib.lib.lfr_debug_poly_prof(out.ctypes.data, 1)
-names = ["coefficients", "first evals", "quadratic", "cubic level", "quartic level", "final evals"]
+names = ["coefficients", "first evals", "grid classify", "extremum cells", "root solves", "final evals"]
 nq, nc = int(out[6]), int(out[7])
 print("quintic calls", nq, "cubic calls", nc, "newton iterations", int(out[8]), "bracket_root calls", int(out[9]))
 for i, nm in enumerate(names):
