@@ -121,7 +121,8 @@ __device__ __forceinline__ EdgeEval eval_edge(const float4 q[5], int kind, doubl
 // forms: a 2x2 solve, or the divided differences of the reduced cubic).  Only
 // the real critical points inside the interval can win the minimisation, and
 // those are bracketed exactly (see real_roots_in).  oracle/lfr_oracle.cc
-// mirrors this operation for operation.
+// mirrors this operation for operation; quartic_roots_grid below is the
+// lane-parallel route to the same quartic roots (the recursion is its fallback).
 // ---------------------------------------------------------------------------
 struct LsSample {
   double x, value, gradient;

@@ -144,7 +144,9 @@ void loss_eval(int kind, double sim, double s, const lfr_options& o,
 // the two lowest coefficients, the others come from a 2x2 solve (closed form) or
 // from the divided differences of the reduced cubic; of the companion-matrix eigenvalues only the real
 // ones inside the interval can win the minimisation, and those are bracketed
-// exactly (real_roots_in).  csrc/lfr_math.cuh mirrors this operation for operation.
+// exactly (real_roots_in).  csrc/lfr_math.cuh mirrors this operation for operation
+// (and additionally has a lane-parallel route to the same quartic roots, checked
+// against this one by the GPU tests).
 // ---------------------------------------------------------------------------
 struct Sample {
   double x = 0, value = 0, gradient = 0;
