@@ -84,7 +84,7 @@ def workload_config(name, p, n_tracks, extra=None):
 
 class ClockSampler:
     """SM clock + throttle reasons DURING the timed region.  The region is tens of
-    milliseconds, so the primary sampler is an NVML thread (pynvml, ~2 ms period);
+    milliseconds, so the primary sampler is an NVML thread (pynvml, back-to-back queries);
     `nvidia-smi -lms` is the fallback when NVML cannot be opened."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -128,10 +128,10 @@ class ClockSampler:
                                 self.reasons.add(nm)
                     except Exception:
                         pass
-                    time.sleep(0.002)
+                    time.sleep(0.0002)   # the NVML queries themselves take a few ms
 
             self.thread = threading.Thread(target=run, daemon=True)
-            self.source = "nvml thread, 2 ms period"
+            self.source = "nvml thread, back-to-back queries"
         except Exception:
             self.thread = None
             try:
@@ -388,7 +388,7 @@ def run_b200(args):
                      "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                      "peak_source": "%s HBM copy bandwidth (burst)" % peak_src,
                      "algorithmic_bytes_per_step": int(alg_bytes), "one_pass_bytes": int(one_pass),
-                     "kernel": "solve_warp_kernel (all size buckets of one step)"},
+                     "kernel": "solve_warp2_kernel / solve_tile_kernel / solve_cta_kernel (all size buckets of one step)"},
         "cpu_baseline": {"value": n_tracks / (cpu_ms / 1e3), "unit": UNIT, "cores": cores, "kind": "port",
                          "ms_per_step": cpu_ms, "single_thread_value": n_tracks / (cpu_1t_ms / 1e3),
                          "single_thread_ms_per_step": cpu_1t_ms,
