@@ -12,8 +12,7 @@ bitwise identical to a 1-GPU solve) plus one all-reduce of the scalar totals.
 """
 from __future__ import annotations
 
-import copy
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, List, Tuple
 
 import numpy as np
 

@@ -38,7 +38,6 @@ def _run_main_with_oracle(monkeypatch, oracle, argv, capsys):
     """Drive cli.main in-process with the GPU solve swapped for the oracle
     (CPU test of everything around the solve)."""
     import lfr_b200.solver as solver
-    import lfr_b200.capi as capi
     monkeypatch.setattr(solver, "solve_problem", lambda p, options=None, positions=None: oracle.solve(p))
     rc = cli.main(argv)
     return rc, capsys.readouterr().out

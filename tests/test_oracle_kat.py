@@ -8,7 +8,6 @@ oracle is checked against before it is trusted as the parity reference.
 import ctypes as C
 
 import numpy as np
-import pytest
 
 from conftest import get_problem
 

@@ -3,7 +3,6 @@ to separate the latency bound of a single small scene from the kernel's
 throughput when the GPU is full."""
 import json, os, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
-import copy
 import numpy as np
 import torch
 from lfr_b200 import build_problem, refined_track_count, synth

@@ -1,6 +1,6 @@
-import os, sys, time
+import os, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
-import numpy as np, torch
+import torch
 from lfr_b200 import build_problem, synth
 from lfr_b200.capi import Plan, load_b200
 lib = load_b200()

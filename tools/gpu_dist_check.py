@@ -1,7 +1,6 @@
 """Sharded multi-GPU solve through the CLI (`solve --gpus N`, NCCL) against the 1-GPU result."""
 import os, subprocess, sys, tempfile
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
-import numpy as np
 from lfr_b200 import synth, wire
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 2

@@ -1,7 +1,7 @@
 import os, sys, time
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
 import ctypes as C
-import numpy as np, torch
+import torch
 import bench
 from lfr_b200.capi import load_b200, Plan
 lib = load_b200()

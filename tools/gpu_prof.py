@@ -1,6 +1,5 @@
 import sys
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 from lfr_b200.capi import load_b200, Plan
 from lfr_b200 import synth, build_problem
 lib = load_b200()
