@@ -289,13 +289,13 @@ __device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const
   const double b0 = si * gi;
   double b = b0;
   bool ok = true;
-  // Gauss-Jordan: the pivot lane normalises its row and broadcasts it through a
-  // double-buffered shared-memory line (one broadcast LDS per element instead of
-  // two shuffles); every other lane eliminates the pivot column from its own row.
-  // The register row is shifted left by one column per step, so slot 0 always
-  // holds the current pivot column and ONE compact loop body serves every column
-  // (a fully unrolled elimination is ~100 KB of straight-line code and stalls on
-  // instruction fetch).
+  // Gauss-Jordan: the pivot lanes publish their raw rows through a double-buffered
+  // shared-memory line (one broadcast LDS.128 per two elements instead of
+  // shuffles); every other lane eliminates the pivot columns from its own row.
+  // The register row is shifted left after every step, so the leading slots
+  // always hold the current pivot columns and ONE compact loop body serves every
+  // step (a fully unrolled elimination is ~100 KB of straight-line code and stalls
+  // on instruction fetch).
   // No per-element guards: all NREG slots are processed every step (slots past
   // the live columns hold zeros), so the step is a straight run of 128-bit
   // shared-memory accesses and DFMAs that the scheduler can overlap freely.
@@ -343,7 +343,7 @@ __device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const
     // rows j, j+1 now read  B [y_j y_j+1]^T = [b_j b_j+1]^T
     const double bp = __shfl_xor_sync(kFull, b, 1);
     y = (i & 1) ? inv0 * bp + inv1 * b : inv0 * b + inv1 * bp;
-  } else {
+  } else {  // scalar pivots (kept for comparison: -DLFR_BLOCK_PIVOT_MAX_NREG=0)
   double myrp = 1.0;
   for (int j = 0; j < n; ++j) {
     double* buf = C.prow + (j & 1) * C.prow_stride;
