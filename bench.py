@@ -92,7 +92,8 @@ class ClockSampler:
 
     def __init__(self, device):
         import threading
-        self.sm, self.reasons, self.smax = [], set(), None
+        self.sm, self.ts, self.reasons, self.smax = [], [], set(), None
+        self.t0 = self.t1 = None   # timed region (perf_counter), set by mark_begin / mark_end
         self.p = self.f = self.thread = None
         self.source = "none"
         self._stop = threading.Event()
@@ -122,6 +123,7 @@ class ClockSampler:
                 while not self._stop.is_set():
                     try:
                         self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        self.ts.append(time.perf_counter())
                         r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                         for nm, bit in names:
                             if r & bit:
@@ -145,9 +147,16 @@ class ClockSampler:
                 self.p = None
 
     def start(self):
-        """Call right before the timed region (the warm-up has already loaded the GPU)."""
+        """Call before the warm-up: the GPU runs the same steps there as in the timed region, and a
+        region of ~10 ms alone may see only one or two NVML answers."""
         if self.thread is not None:
             self.thread.start()
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.thread is not None:
@@ -179,9 +188,11 @@ class ClockSampler:
             os.unlink(self.f.name)
         else:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
+        in_timed = sum(1 for t in self.ts if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(smax)) if smax else None, "reasons": sorted(self.reasons),
-                "samples": len(sm), "source": self.source}
+                "samples": len(sm), "samples_in_timed_region": in_timed,
+                "window": "warm-up + device-timed region", "source": self.source}
 
 
 def pinned_problem(lib, p):
@@ -287,30 +298,34 @@ def run_b200(args):
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     plan = Plan(lib, p, opts)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         plan.solve(stream)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     # ---- value: device-resident, CUDA events per step ---------------------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    if sampler:
+        sampler.mark_begin()
     for a, b in ev:
         flush.zero_()
         a.record()
         plan.solve(stream)
         b.record()
     barrier()
+    if sampler:
+        sampler.mark_end()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_per_step = float(np.mean(step_ms))
     ms_per_step_median = float(np.median(step_ms))
     _, st = plan.download(stream)
     alg_bytes, one_pass = plan.traffic(stream)
     launches = plan.num_launches()
-    # clocks are sampled over the device-timed region only; the sampler stops before the host-timed
-    # e2e leg so that its polling cannot perturb it
+    # clocks are sampled over warm-up + the device-timed region; the sampler stops before the
+    # host-timed e2e leg so that its polling cannot perturb it
     clocks = sampler.stop() if sampler else None
     # ---- e2e: C-ABI call with pinned host buffers ------------------------------------------
     s2, keep, pos_pinned, h2d = pinned_problem(lib, p)
