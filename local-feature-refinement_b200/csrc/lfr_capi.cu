@@ -41,6 +41,9 @@ int cuda_code(cudaError_t e) {
   } while (0)
 
 constexpr int kMaxSmemPerBlock = 227 * 1024;
+// Components with more unknowns than this (and <= 32) take the two-warp tile kernel <64, 32> instead of
+// the one-warp register kernel; 32 = never.  Overridden per plan by LFR_TILE_FROM_N.
+constexpr int kTileFromDefault = 32;
 constexpr int kMaxStreams = 12;
 
 lfr::DevConsts make_consts(const lfr_options& o) {
@@ -215,10 +218,16 @@ int upload(DevBuf* d, const T* h, size_t count, cudaStream_t s) {
 int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   static const int kClass[] = {2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 57344, kMaxSmemPerBlock};
   const int n_class = sizeof(kClass) / sizeof(kClass[0]);
-  // register warp kernel (8..32), register tile kernel (48, 64: 64 threads; 80: 128 threads), smem-Cholesky warp kernel (0)
-  static const int kVariant[8] = {8, 16, 24, 32, 48, 64, 80, 0};
-  const int kNV = 8;
+  // register warp kernel (8..32), register tile kernel (132 = 64 threads x NREG 32; 48, 64: 64 threads;
+  // 80: 128 threads), smem-Cholesky warp kernel (0)
+  static const int kVariant[9] = {8, 16, 24, 32, 132, 48, 64, 80, 0};
+  const int kNV = 9, kV1 = 8;
+  auto is_tile = [](int vi) { return vi >= 4 && vi <= 7; };
   const bool no_tile = getenv("LFR_NO_TILE") != nullptr;
+  // components with more than LFR_TILE_FROM_N unknowns (and <= 32) go to the two-warp tile kernel
+  // instead of the one-warp kernel (their edge evaluation is split over 64 threads)
+  const char* tf = getenv("LFR_TILE_FROM_N");
+  const int tile_from = no_tile ? 32 : (tf ? atoi(tf) : kTileFromDefault);
   std::vector<std::vector<uint32_t>> members(kNV * n_class);
   std::vector<Bucket> caps(kNV * n_class);
   pl->comp_size.resize(p->n_components);
@@ -251,11 +260,12 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       continue;
     }
     const int e = std::max<int>(1, (int)eup);
-    int vi = (n2 <= 8) ? 0 : (n2 <= 16 ? 1 : (n2 <= 24 ? 2 : (n2 <= 32 ? 3 : (n2 <= 48 ? 4 : (n2 <= 64 ? 5 : (n2 <= 80 ? 6 : 7))))));
-    if (vi >= 4 && vi <= 6 && (no_tile || lfr::TileLayout(e, (int)nc, n2).total > kMaxSmemPerBlock)) vi = 7;
-    if (force_v1) vi = 7;
-    const int need = (vi == 7) ? lfr::WarpLayout(e, (int)nc, n2).total
-                     : (vi >= 4 ? lfr::TileLayout(e, (int)nc, n2).total : lfr::Warp2Layout(e, (int)nc, n2).total);
+    int vi = (n2 <= 8) ? 0 : (n2 <= 16 ? 1 : (n2 <= 24 ? 2 : (n2 <= 32 ? 3 : (n2 <= 48 ? 5 : (n2 <= 64 ? 6 : (n2 <= 80 ? 7 : kV1))))));
+    if (vi <= 3 && n2 > tile_from && lfr::TileLayout(e, (int)nc, n2).total <= kMaxSmemPerBlock) vi = 4;
+    if (vi >= 5 && is_tile(vi) && (no_tile || lfr::TileLayout(e, (int)nc, n2).total > kMaxSmemPerBlock)) vi = kV1;
+    if (force_v1) vi = kV1;
+    const int need = (vi == kV1) ? lfr::WarpLayout(e, (int)nc, n2).total
+                     : (is_tile(vi) ? lfr::TileLayout(e, (int)nc, n2).total : lfr::Warp2Layout(e, (int)nc, n2).total);
     int k = 0;
     while (k < n_class && need > kClass[k]) ++k;
     if (k == n_class) return fail(LFR_EUNSUPPORTED, "component needs more shared memory than one SM has");
@@ -273,9 +283,9 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       b.variant = kVariant[vi];
       b.n = (uint32_t)mem.size();
       b.offset = (uint32_t)pl->list_host.size();
-      b.smem_per_warp = (vi == 7) ? lfr::WarpLayout(b.emax, b.ncmax, b.n2max).total
-                        : (vi >= 4 ? lfr::TileLayout(b.emax, b.ncmax, b.n2max).total
-                                   : lfr::Warp2Layout(b.emax, b.ncmax, b.n2max).total);
+      b.smem_per_warp = (vi == kV1) ? lfr::WarpLayout(b.emax, b.ncmax, b.n2max).total
+                        : (is_tile(vi) ? lfr::TileLayout(b.emax, b.ncmax, b.n2max).total
+                                       : lfr::Warp2Layout(b.emax, b.ncmax, b.n2max).total);
       if (b.smem_per_warp > kMaxSmemPerBlock) return fail(LFR_EUNSUPPORTED, "bucket exceeds shared memory");
       b.warps = (4 * b.smem_per_warp <= kMaxSmemPerBlock) ? 4 : 1;
       if (b.variant >= 48) b.warps = 1;  // tile kernels: one component per CTA
@@ -480,6 +490,8 @@ int set_kernel_attrs() {
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp2_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_tile_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_tile_kernel<64, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_tile_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -545,7 +557,9 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
     wb.smem_per_warp = b.smem_per_warp;
     const size_t smem = (size_t)b.smem_per_warp * b.warps;
     const unsigned grid = (b.n + b.warps - 1) / b.warps;
-    if (b.variant == 48)
+    if (b.variant == 132)
+      lfr::solve_tile_kernel<64, 32><<<b.n, 64, smem, bs>>>(P, pl->K, wb);
+    else if (b.variant == 48)
       lfr::solve_tile_kernel<64, 48><<<b.n, 64, smem, bs>>>(P, pl->K, wb);
     else if (b.variant == 64)
       lfr::solve_tile_kernel<64, 64><<<b.n, 64, smem, bs>>>(P, pl->K, wb);
