@@ -113,12 +113,15 @@ def test_duplicate_pairs_take_the_serial_assembly_path(b200, oracle):
     assert np.array_equal(st_g["iterations"], st_o["iterations"])
 
 
-@pytest.mark.parametrize("env,cfg", [("LFR_FORCE_V1", "cfg1"), ("LFR_FORCE_V1", "cfg3"), ("LFR_NO_TILE", "cfg4")])
+@pytest.mark.parametrize("env,cfg", [("LFR_FORCE_V1", "cfg1"), ("LFR_FORCE_V1", "cfg3"), ("LFR_NO_TILE", "cfg4"),
+                                     ("LFR_TILE_FROM_N", "cfg2")])
 def test_fallback_tiers_match_oracle(b200, oracle, monkeypatch, env, cfg):
     """The shared-memory Cholesky warp kernel (solve_warp_kernel) is the tier for
     80 < n <= 96 unknowns and the fallback behind the register kernels; the
     schedule reads LFR_FORCE_V1 / LFR_NO_TILE per plan, so the same scenes can be
-    sent through it (cfg4 without the tile tier: v1 for 32 < n <= 96)."""
+    sent through it (cfg4 without the tile tier: v1 for 32 < n <= 96).  LFR_TILE_FROM_N=1
+    routes every component with n <= 32 to the two-warp tile kernel <64, 32> instead of the
+    one-warp kernel."""
     monkeypatch.setenv(env, "1")
     _, p = get_problem(cfg)
     _compare(b200, oracle, p)
