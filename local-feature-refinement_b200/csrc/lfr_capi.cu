@@ -871,4 +871,25 @@ int lfr_debug_quartic_roots(const double* coef, const double* lohi, uint64_t n, 
   return rc;
 }
 
+/* test hook: the line search's interpolating-polynomial minimiser on n cases of 11 doubles
+   {f0, g0, x1, f1, g1, three, x2, f2, g2, lo, hi}; out[n] = selected step size */
+int lfr_debug_ls_minimizer(const double* cases, uint64_t n, double* out) {
+  lfr_options o;
+  lfr_options_default(&o);
+  LFR_TRY(select_device(o));
+  if (n == 0) return LFR_OK;
+  DevBuf d_i, d_o;
+  auto run = [&]() -> int {
+    LFR_TRY(upload(&d_i, cases, 11 * n, 0));
+    LFR_TRY(d_o.reserve(n * 8));
+    lfr::ls_minimizer_kernel<<<(unsigned)((n + 3) / 4), 128>>>(d_i.as<double>(), (int)n, d_o.as<double>());
+    LFR_CUDA(cudaGetLastError());
+    LFR_CUDA(cudaMemcpy(out, d_o.p, n * 8, cudaMemcpyDeviceToHost));
+    return LFR_OK;
+  };
+  const int rc = run();
+  d_i.release(); d_o.release();
+  return rc;
+}
+
 }  // extern "C"

@@ -636,6 +636,17 @@ __global__ void local_index_kernel(const uint32_t* comp_ptr, const uint32_t* com
   local_of[comp_nodes[i]] = i - comp_ptr[lo];
 }
 
+// Test hook: the line search's step-size selection (hermite_minimizer) on caller-supplied
+// samples, one warp per case (lfr_debug_ls_minimizer).  in[c] = {f0, g0, x1, f1, g1, three,
+// x2, f2, g2, lo, hi}.
+__global__ void ls_minimizer_kernel(const double* __restrict__ in, int n, double* __restrict__ out) {
+  const int wid = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (wid >= n) return;  // whole warps leave together
+  const double* s = in + 11 * (size_t)wid;
+  const double x = hermite_minimizer(s[0], s[1], s[2], s[3], s[4], s[5] != 0.0, s[6], s[7], s[8], s[9], s[10], lane);
+  if (lane == 0) out[wid] = x;
+}
+
 // Test hook: the line search's quartic root finders on caller-supplied polynomials,
 // one warp per polynomial (lfr_debug_quartic_roots).
 __global__ void quartic_roots_kernel(const double* __restrict__ coef, const double* __restrict__ lohi, int n,

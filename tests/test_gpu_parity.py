@@ -211,6 +211,90 @@ def test_quartic_root_finders_agree(b200, oracle):
     assert (res[1][1] > 0).mean() > 0.4 and (res[1][1] >= 3).sum() > 100   # the cases do exercise multi-root cells
 
 
+def _ls_cases(rng, n):
+    """Line-search states {f0, g0, x1, f1, g1, three, x2, f2, g2, lo, hi}: random ones in Ceres'
+    contraction range, and degenerate ones whose interpolant loses its leading coefficients
+    exactly (samples of an exact quadratic / cubic with dyadic data -> the generic,
+    leading-zero-stripping route of hermite_minimizer)."""
+    rows = []
+    for k in range(n):
+        three = k % 2 == 1
+        x2 = 10.0 ** rng.uniform(-3, 0)
+        x1 = x2 * (rng.uniform(0.02, 0.6) if three else 1.0)
+        if k % 10 < 8:
+            f0, g0 = rng.normal(), -abs(rng.normal())
+            f1, g1, f2, g2 = rng.normal(size=4) * np.array([1.0, 3.0 / x1, 1.0, 3.0 / x2])
+        else:
+            # exact low-degree polynomial, dyadic coefficients and abscissae
+            x2 = 2.0 ** -int(rng.integers(0, 6))
+            x1 = x2 * (0.5 if three else 1.0)
+            deg = 2 if k % 10 == 8 else 3
+            co = np.concatenate([np.zeros(3 - deg), rng.integers(-4, 5, size=deg + 1).astype(float)])
+            if co[-2] >= 0:
+                co[-2] = -1.0                      # descent direction at 0
+            pl = np.poly1d(co)
+            f0, g0 = pl(0.0), pl.deriv()(0.0)
+            f1, g1, f2, g2 = pl(x1), pl.deriv()(x1), pl(x2), pl.deriv()(x2)
+        rows.append([f0, g0, x1, f1, g1, 1.0 if three else 0.0, x2 if three else 0.0, f2 if three else 0.0,
+                     g2 if three else 0.0, 1e-3 * x1, 0.6 * x1])
+    return np.ascontiguousarray(rows, dtype=np.float64)
+
+
+def _ls_reference_poly(row):
+    f0, g0, x1, f1, g1, three, x2, f2, g2, lo, hi = row
+    pts = [(0.0, f0, g0), (x1, f1, g1)] + ([(x2, f2, g2)] if three else [])
+    h = max(p[0] for p in pts)
+    deg = 2 * len(pts) - 1
+    A, b = [], []
+    for (x, f, g) in pts:
+        t = x / h
+        A.append([t ** k for k in range(deg, -1, -1)])
+        b.append(f)
+        A.append([k * t ** (k - 1) if k > 0 else 0.0 for k in range(deg, -1, -1)])
+        b.append(g * h)
+    co = np.linalg.solve(np.array(A), np.array(b))
+    return np.poly1d(co), h
+
+
+def _check_ls(cases, x_test, x_oracle):
+    same = np.isclose(x_test, x_oracle, rtol=1e-8, atol=0.0)
+    for k in np.nonzero(~same)[0]:
+        # a different abscissa is acceptable only where the interpolant takes the same value
+        # (two candidates tie to rounding)
+        pl, h = _ls_reference_poly(cases[k])
+        scale = max(1.0, np.abs(pl.coeffs).max())
+        assert abs(pl(x_test[k] / h) - pl(x_oracle[k] / h)) <= 1e-10 * scale, (k, x_test[k], x_oracle[k])
+    assert same.mean() >= 0.995, same.mean()
+    lo, hi = cases[:, 9], cases[:, 10]
+    assert np.all((x_test >= lo) & (x_test <= hi))
+
+
+def _oracle_ls(oracle, cases):
+    import ctypes as C
+    out = np.zeros(cases.shape[0])
+    x, v = C.c_double(), C.c_double()
+    for k, r in enumerate(cases):
+        three = r[5] != 0.0
+        smp = [[0.0, r[0], r[1], 1, 1], [r[2], r[3], r[4], 1, 1]] + ([[r[6], r[7], r[8], 1, 1]] if three else [])
+        a = np.array(smp, dtype=np.float64)
+        oracle.lib.lfr_ref_minimize_interpolating_polynomial(a.ctypes.data, len(smp), float(r[9]), float(r[10]),
+                                                             C.byref(x), C.byref(v))
+        out[k] = x.value
+    return out
+
+
+def test_ls_minimizer_matches_oracle(b200, oracle):
+    """The whole step-size selection of the Armijo line search (interpolant, critical
+    points, candidate scan) on the GPU against the oracle, case by case."""
+    import ctypes as C
+    cases = _ls_cases(np.random.default_rng(4321), 5000)
+    f = b200.lib.lfr_debug_ls_minimizer
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    xg = np.zeros(cases.shape[0])
+    assert f(cases.ctypes.data, cases.shape[0], xg.ctypes.data) == 0
+    _check_ls(cases, xg, _oracle_ls(oracle, cases))
+
+
 def test_cta_pcg_tier_on_large_components(b200, oracle):
     """Components with more than 96 unknowns (ring scene, up to 60 nodes) take the
     CTA tier: matrix-free block-Jacobi PCG to 1e-13 stands in for the exact solve."""
