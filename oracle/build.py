@@ -13,16 +13,18 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "lfr_oracle.cc")
+# the literal polynomial.cc restatement lives with the Ceres shim (oracle/ref_shims/)
+SHIMS = os.path.join(HERE, "ref_shims")
+MINI_CERES = os.path.join(SHIMS, "mini_ceres.cc")
 OUT = os.path.join(HERE, "liblfr_ref.so")
 
 
 def build(force: bool = False) -> str:
-    if (not force and os.path.exists(OUT)
-            and os.path.getmtime(OUT) >= os.path.getmtime(SRC)
-            and os.path.getmtime(OUT) >= os.path.getmtime(os.path.join(HERE, "..", "include", "lfr.h"))):
+    deps = [SRC, MINI_CERES, os.path.join(SHIMS, "ceres", "ceres.h"), os.path.join(HERE, "..", "include", "lfr.h")]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
-           "-Wall", "-Wextra", "-o", OUT, SRC]
+           "-Wall", "-Wextra", "-I", SHIMS, "-o", OUT, SRC, MINI_CERES]
     subprocess.check_call(cmd)
     return OUT
 

@@ -6,12 +6,17 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // do, and only as the checker or the timed CPU baseline.
 //
-// PARITY UNPINNED.  The arithmetic of the reference's hot path lives in Ceres
-// Solver (un-vendored, version unpinned by the reference; CMakeLists.txt:9
-// `find_package(Ceres REQUIRED)`, `-std=c++11` => Ceres 1.13/1.14 era) and
-// neither Ceres, Eigen, COLMAP, Boost nor protoc exist in this image, so the
-// reference cannot be built here (oracle/_ref is not buildable) and it ships no
-// tests or golden vectors.  This file therefore restates
+// PARITY: PINNED AT THE REFERENCE'S OWN SOURCES, UNPINNED INSIDE CERES.  The
+// arithmetic of the reference's hot path lives in Ceres Solver (un-vendored,
+// version unpinned by the reference; CMakeLists.txt:9 `find_package(Ceres
+// REQUIRED)`, `-std=c++11` => Ceres 1.13/1.14 era); neither Ceres, Eigen,
+// COLMAP, Boost nor protoc exist in this image and the reference ships no tests
+// or golden vectors.  What IS pinned: interpolate() / the residual and its
+// Jacobian are bitwise equal to the reference's cost.cc compiled unmodified
+// against shim headers (oracle/_ref/libref_cost.so, tests/test_ref_cost.py), and
+// the whole pipeline is compared with the reference's solve.cc compiled the same
+// way (oracle/_ref/solve, tests/test_ref_solve.py).  What is NOT: the internals
+// of Ceres itself (no Ceres binary to run).  This file restates
 //   * multi-view-refinement/cost.cc:13-48   (BiquadraticInterpolator::Evaluate)
 //   * multi-view-refinement/cost.cc:78-90   (InterpolatedCostFunctor)
 //   * multi-view-refinement/solve.cc:79-160 (create_and_solve_problem)
@@ -37,11 +42,13 @@
 #include <complex>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../include/lfr.h"
+#include "ceres/ceres.h"  // oracle/ref_shims: the literal polynomial.cc restatement (ceres::shim)
 
 namespace {
 
@@ -158,6 +165,21 @@ double poly_eval(const double* p, int n, double x) {
   for (int i = 0; i < n; ++i) v = v * x + p[i];
   return v;
 }
+
+// Line-search interpolation mode.
+//   0 (default) LITERAL: Ceres' polynomial.cc as written — Vandermonde system in the raw step
+//     sizes solved by full-pivot LU, critical points = real parts of ALL eigenvalues of the
+//     balanced companion matrix (ceres::shim::MinimizeInterpolatingPolynomial in
+//     oracle/ref_shims/mini_ceres.cc).  This is what the GPU is compared with.
+//   1 FAST: the normalised-variable / bracketed-real-roots formulation below, which the CUDA
+//     path mirrors operation for operation (lfr_math.cuh).  Kept so that the two can be compared
+//     state by state (tests/test_linesearch_modes.py).
+std::atomic<int> g_ls_mode(0);
+// Optional recording of every line-search interpolation state {f0, g0, x1, f1, g1, three, x2, f2,
+// g2, lo, hi} (the input format of lfr_debug_ls_minimizer) for the mode-comparison tests.
+std::atomic<bool> g_harvest(false);
+std::mutex g_harvest_mutex;
+std::vector<double> g_harvested;
 
 // ---- real roots of a polynomial inside an interval ---------------------------
 // MinimizePolynomial looks at the real parts of ALL roots of p', but a candidate
@@ -557,8 +579,38 @@ void do_line_search(const Component& C, const lfr_options& o,
     const double min_step = o.max_line_search_step_contraction * current.x;
     const double max_step = o.min_line_search_step_contraction * current.x;
     double step_size;
-    if (!current.value_valid || !current.gradient_valid ||
-        (previous.value_valid && !previous.gradient_valid)) {
+    if (g_harvest.load() && current.value_valid && current.gradient_valid &&
+        !(previous.value_valid && !previous.gradient_valid)) {
+      const double st[11] = {initial.value, initial.gradient, current.x, current.value, current.gradient,
+                             previous.value_valid ? 1.0 : 0.0, previous.x, previous.value, previous.gradient,
+                             min_step, max_step};
+      std::lock_guard<std::mutex> lock(g_harvest_mutex);
+      g_harvested.insert(g_harvested.end(), st, st + 11);
+    }
+    if (g_ls_mode.load() == 0) {
+      // LineSearch::InterpolatingPolynomialMinimizingStepSize, CUBIC: bisection only for an invalid
+      // value; otherwise interpolate {lower bound, current [, previous]} with whatever is valid
+      if (!current.value_valid) {
+        step_size = std::min(std::max(current.x * 0.5, min_step), max_step);
+      } else {
+        double smp[15];
+        int ns = 0;
+        auto push = [&](const Sample& q) {
+          smp[5 * ns] = q.x;
+          smp[5 * ns + 1] = q.value;
+          smp[5 * ns + 2] = q.gradient;
+          smp[5 * ns + 3] = q.value_valid ? 1.0 : 0.0;
+          smp[5 * ns + 4] = q.gradient_valid ? 1.0 : 0.0;
+          ++ns;
+        };
+        push(initial);
+        push(current);
+        if (previous.value_valid) push(previous);
+        double unused = 0.0;
+        ceres::shim::MinimizeInterpolatingPolynomial(smp, ns, min_step, max_step, &step_size, &unused);
+      }
+    } else if (!current.value_valid || !current.gradient_valid ||
+               (previous.value_valid && !previous.gradient_valid)) {
       // invalid sample (a non-finite gradient with a finite value needs overflow): bisection rule
       step_size = std::min(std::max(current.x * 0.5, min_step), max_step);
     } else {
@@ -830,9 +882,13 @@ SolveResult minimize(Component& C, const lfr_options& o) {
   }
   R.iterations = iteration;
   R.final_cost = minimum_cost;
-  for (int f = 0; f < C.n_free; ++f) {  // parameters <- best x
-    C.pos[2 * C.local_of_free[f]] = best[2 * f];
-    C.pos[2 * C.local_of_free[f] + 1] = best[2 * f + 1];
+  // solver.cc (Minimize): the user state is only overwritten when Summary::IsSolutionUsable(),
+  // i.e. not after FAILURE (10 consecutive invalid steps) — then the ORIGINAL values stay.
+  if (R.termination != LFR_TERM_FAILURE) {
+    for (int f = 0; f < C.n_free; ++f) {  // parameters <- best x
+      C.pos[2 * C.local_of_free[f]] = best[2 * f];
+      C.pos[2 * C.local_of_free[f] + 1] = best[2 * f + 1];
+    }
   }
   return R;
 }
@@ -1057,10 +1113,47 @@ void lfr_ref_loss(int kind, double sim, double s, const lfr_options* opt, double
 void lfr_ref_minimize_interpolating_polynomial(const double* samples, int n, double x_min,
                                                double x_max, double* optimal_x,
                                                double* optimal_value) {
+  if (g_ls_mode.load() == 0) {  // literal polynomial.cc
+    ceres::shim::MinimizeInterpolatingPolynomial(samples, n, x_min, x_max, optimal_x, optimal_value);
+    return;
+  }
   const bool three = n >= 3;
   *optimal_x = hermite_minimizer(samples[1], samples[2], samples[5], samples[6], samples[7], three,
                                  three ? samples[10] : 0.0, three ? samples[11] : 0.0,
                                  three ? samples[12] : 0.0, x_min, x_max, optimal_value);
+}
+
+// line-search interpolation mode: 0 literal polynomial.cc (default), 1 the fast formulation the GPU mirrors
+void lfr_ref_set_line_search_mode(int mode) { g_ls_mode.store(mode ? 1 : 0); }
+int lfr_ref_get_line_search_mode(void) { return g_ls_mode.load(); }
+
+// the FAST formulation, whatever the mode (same arguments as lfr_ref_minimize_interpolating_polynomial)
+void lfr_ref_minimize_interpolating_polynomial_fast(const double* samples, int n, double x_min, double x_max,
+                                                    double* optimal_x, double* optimal_value) {
+  const bool three = n >= 3;
+  *optimal_x = hermite_minimizer(samples[1], samples[2], samples[5], samples[6], samples[7], three,
+                                 three ? samples[10] : 0.0, three ? samples[11] : 0.0,
+                                 three ? samples[12] : 0.0, x_min, x_max, optimal_value);
+}
+
+// polynomial.cc FindPolynomialRoots, literal (balanced companion matrix eigenvalues): real and imaginary
+// parts of all roots of coeffs[0..n) (highest degree first); returns the count or -1
+int lfr_ref_find_polynomial_roots(const double* coeffs, int n, double* real, double* imag) {
+  return ceres::shim::FindPolynomialRoots(coeffs, n, real, imag);
+}
+
+// harvest of line-search interpolation states (11 doubles each) from subsequent lfr_solve calls
+void lfr_ref_harvest(int on) {
+  std::lock_guard<std::mutex> lock(g_harvest_mutex);
+  g_harvested.clear();
+  g_harvest.store(on != 0);
+}
+uint64_t lfr_ref_harvest_take(double* out, uint64_t max_states) {
+  std::lock_guard<std::mutex> lock(g_harvest_mutex);
+  const uint64_t have = g_harvested.size() / 11;
+  const uint64_t n = std::min(have, max_states);
+  if (out && n) std::memcpy(out, g_harvested.data(), sizeof(double) * 11 * n);
+  return have;
 }
 
 // real roots inside [lo, hi] of a polynomial given highest-degree-first (n <= 5 coefficients)

@@ -269,30 +269,45 @@ def _check_ls(cases, x_test, x_oracle):
     assert np.all((x_test >= lo) & (x_test <= hi))
 
 
-def _oracle_ls(oracle, cases):
-    import ctypes as C
-    out = np.zeros(cases.shape[0])
-    x, v = C.c_double(), C.c_double()
-    for k, r in enumerate(cases):
-        three = r[5] != 0.0
-        smp = [[0.0, r[0], r[1], 1, 1], [r[2], r[3], r[4], 1, 1]] + ([[r[6], r[7], r[8], 1, 1]] if three else [])
-        a = np.array(smp, dtype=np.float64)
-        oracle.lib.lfr_ref_minimize_interpolating_polynomial(a.ctypes.data, len(smp), float(r[9]), float(r[10]),
-                                                             C.byref(x), C.byref(v))
-        out[k] = x.value
-    return out
+def _oracle_ls(oracle, cases, fast):
+    from oracle_util import minimize_interpolating
+    return minimize_interpolating(oracle, cases, fast=fast)
 
 
 def test_ls_minimizer_matches_oracle(b200, oracle):
     """The whole step-size selection of the Armijo line search (interpolant, critical
-    points, candidate scan) on the GPU against the oracle, case by case."""
+    points, candidate scan) on the GPU, case by case: against the oracle's FAST formulation (which
+    the kernel mirrors operation for operation) on every state, and against the LITERAL
+    polynomial.cc restatement (Vandermonde full-pivot LU + companion-matrix eigenvalues) on the
+    states where Ceres' own fit keeps full numerical rank."""
     import ctypes as C
+    from oracle_util import well_conditioned
     cases = _ls_cases(np.random.default_rng(4321), 5000)
     f = b200.lib.lfr_debug_ls_minimizer
     f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
     xg = np.zeros(cases.shape[0])
     assert f(cases.ctypes.data, cases.shape[0], xg.ctypes.data) == 0
-    _check_ls(cases, xg, _oracle_ls(oracle, cases))
+    _check_ls(cases, xg, _oracle_ls(oracle, cases, fast=True))
+    wc = well_conditioned(cases)
+    assert wc.sum() > 1000
+    _check_ls(cases[wc], xg[wc], _oracle_ls(oracle, cases[wc], fast=False))
+
+
+def test_ls_minimizer_on_harvested_states_matches_literal_oracle(b200, oracle):
+    """Every interpolation state the line searches of cfg2 and the contraction fixture actually go
+    through: the GPU's step equals the literal oracle's wherever Ceres' fit is well conditioned."""
+    import ctypes as C
+    from oracle_util import harvest_line_search_states, well_conditioned
+    f = b200.lib.lfr_debug_ls_minimizer
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    for name, scale in (("cfg2", 1.0), ("cfg4", 0.5), ("ring60", 1.0)):
+        _, p = get_problem(name, scale=scale)
+        _, _, states = harvest_line_search_states(oracle, p, oracle.default_options(n_threads=8))
+        states = np.ascontiguousarray(states[well_conditioned(states)])
+        assert states.shape[0] > 10
+        xg = np.zeros(states.shape[0])
+        assert f(states.ctypes.data, states.shape[0], xg.ctypes.data) == 0
+        _check_ls(states, xg, _oracle_ls(oracle, states, fast=False))
 
 
 def test_cta_pcg_tier_on_large_components(b200, oracle):
