@@ -284,7 +284,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = load_b200()
-    opts = lib.default_options(device=local)
+    opts = lib.default_options(device=local, debug_flags=args.debug_flags)
     # weak scaling: rank r solves its own scene (seed offset), same shape
     from lfr_b200 import synth
     base_seed = synth.CONFIGS[synth.ALIASES.get(args.workload, args.workload)].seed
@@ -424,6 +424,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--debug-flags", type=int, default=0,
+                    help="lfr_options.debug_flags for A/B experiments (LFR_DBG_*; 0 = the product path)")
     args = ap.parse_args()
     args.workload = {"fountain": "cfg2", "herzjesu": "cfg3"}.get(args.workload, args.workload)
     if args.impl == "reference":

@@ -117,8 +117,18 @@ typedef struct lfr_options {
   int32_t n_threads;     /* CPU oracle: pool threads (solve.cc:384,617). b200: ignored */
   int32_t device;        /* b200: CUDA device ordinal; oracle: ignored      */
   int32_t linear_solver; /* 0 auto, 1 dense Cholesky, 2 block-Jacobi PCG (b200 only) */
-  int32_t reserved;
+  int32_t debug_flags;   /* LFR_DBG_* test / profiling hooks; 0 in production      */
 } lfr_options;
+
+/* lfr_options.debug_flags (b200 only): route components through the fallback tiers, switch the
+ * staging / zero-copy mechanisms off, collect per-component cycle counters.  Results do not
+ * depend on them (tests/test_gpu_parity.py). */
+#define LFR_DBG_FORCE_SMEM_CHOLESKY 0x1 /* every warp-tier component through the shared-memory Cholesky kernel */
+#define LFR_DBG_NO_TILE 0x2             /* no 64/128-thread tile kernels                                       */
+#define LFR_DBG_STAGE_LDG 0x4           /* stage edge records with LDG -> STS instead of TMA bulk copies       */
+#define LFR_DBG_NO_ZERO_COPY 0x8        /* lfr_solve(): copy edges / positions through HBM even when the caller's buffers are pinned */
+#define LFR_DBG_PROFILE 0x10            /* per-component clock64() counters (lfr_debug_plan_cycles)            */
+#define LFR_DBG_TILE_FROM_SHIFT 8       /* bits 8..15 = n: components with more than n unknowns (n <= 32) use the two-warp tile kernel */
 
 /* Optional per-component results, caller-owned, indexed like comp_ptr. Any
  * pointer may be NULL. */
@@ -145,8 +155,14 @@ void lfr_options_default(lfr_options* o);
  * Solve every component of size > 1.  `positions` is [2*n_nodes] doubles,
  * (row, col) per node (cost.cc:83): in = initial values (the reference passes
  * zeros, solve.cc:609-612), out = refined displacements; entries of nodes that
- * are roots, or in components of size 1, are left untouched.
- * Replaces solve.cc:614-635.  Host pointers; host<->device copies inside.
+ * are roots, or in components of size 1, are left untouched, and so is a
+ * component whose solve ends in LFR_TERM_FAILURE (Ceres only commits a usable
+ * solution).  Replaces solve.cc:614-635.  Host pointers; host<->device traffic
+ * inside the call.  b200: when `p->edges` / `positions` are page-locked host
+ * memory (cudaHostAlloc / cudaHostRegister, 16-byte aligned) the kernels pull
+ * each component's edge records straight from the caller's buffer into shared
+ * memory (zero-copy over PCIe, overlapped with the solves) and write the
+ * results straight back; pageable buffers are copied through HBM.
  */
 int lfr_solve(const lfr_problem* p, const lfr_options* o, double* positions,
               lfr_stats* stats);

@@ -19,6 +19,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 B200_LIB_PATH = os.path.join(HERE, "csrc", "liblfr_b200.so")
 
 LFR_OK = 0
+# lfr_options.debug_flags (include/lfr.h)
+DBG_FORCE_SMEM_CHOLESKY, DBG_NO_TILE, DBG_STAGE_LDG, DBG_NO_ZERO_COPY, DBG_PROFILE = 0x1, 0x2, 0x4, 0x8, 0x10
+DBG_TILE_FROM_SHIFT = 8
 TERM_NAMES = {0: "skipped", 1: "gradient_tol", 2: "parameter_tol", 3: "function_tol",
               4: "min_radius", 5: "no_convergence", 6: "failure", 7: "empty"}
 
@@ -46,7 +49,7 @@ class LfrOptions(C.Structure):
         ("max_line_search_step_contraction", C.c_double),
         ("min_line_search_step_contraction", C.c_double), ("min_line_search_step_size", C.c_double),
         ("n_threads", C.c_int32), ("device", C.c_int32), ("linear_solver", C.c_int32),
-        ("reserved", C.c_int32),
+        ("debug_flags", C.c_int32),
     ]
 
 

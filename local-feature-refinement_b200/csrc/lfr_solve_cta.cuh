@@ -575,9 +575,12 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
       nu *= 2.0;
     }
   }
-  for (int i = tid; i < C.n; i += kCtaThreads) {
-    const int l = C.lof[i >> 1];
-    P.positions[2 * (size_t)C.node[l] + (i & 1)] = C.x[2 * l + (i & 1)];
+  // (not after FAILURE: Ceres only commits a usable solution, solver.cc Minimize / IsSolutionUsable)
+  if (term != LFR_TERM_FAILURE) {
+    for (int i = tid; i < C.n; i += kCtaThreads) {
+      const int l = C.lof[i >> 1];
+      P.positions_out[2 * (size_t)C.node[l] + (i & 1)] = C.x[2 * l + (i & 1)];
+    }
   }
   if (tid == 0) {
     P.st_iter[c] = iter;

@@ -12,6 +12,7 @@
 namespace lfr {
 
 struct TileLayout {
+  int stage, bar;
   int x, xc, g, S, dl, H, scr, tup, prow, red, hdr;
   int eidx, meta, node, rowstart, candptr, cnt;
   int twin, outptr, freeof, lof;
@@ -19,6 +20,8 @@ struct TileLayout {
   __host__ __device__ TileLayout(int emax, int ncmax, int n2max) {
     ldh = n2max | 1;
     int o = 0;
+    stage = o; o += 80 * emax;   // staged edge records (see Warp2Layout)
+    bar = o; o += 16;
     x = o; o += 16 * ncmax;
     xc = o; o += 16 * ncmax;
     g = o; o += 8 * n2max;
@@ -53,7 +56,8 @@ struct TileCtx {
   uint32_t *eidx, *meta, *node;
   uint16_t *twin, *outptr, *lof;
   int16_t* freeof;
-  const float4* edges;
+  float4* stage;
+  uint64_t* bar;
 };
 
 template <int T>
@@ -103,10 +107,10 @@ __device__ __forceinline__ double tile_eval(const TileCtx<T>& C, const double* x
   for (int j = C.tid; j < C.Ec; j += T) {
     const uint32_t mt = C.meta[j];
     const int s = mt & 0xfff, d = (mt >> 12) & 0xfff, kind = mt >> 24;
-    const float4* qp = C.edges + 5 * (size_t)C.eidx[j];
+    const float4* qp = C.stage + 5 * C.eidx[j];
     float4 q[5];
 #pragma unroll
-    for (int t = 0; t < 5; ++t) q[t] = __ldg(qp + t);
+    for (int t = 0; t < 5; ++t) q[t] = qp[t];
     const EdgeEval ev = eval_edge(q, kind, xe[2 * s], xe[2 * s + 1], xe[2 * d], xe[2 * d + 1], K);
     double* sc = C.scr + j;
     sc[0] = ev.a;
@@ -383,7 +387,8 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   C.outptr = (uint16_t*)(base + L.outptr);
   C.freeof = (int16_t*)(base + L.freeof);
   C.lof = (uint16_t*)(base + L.lof);
-  C.edges = P.edges;
+  C.stage = (float4*)(base + L.stage);
+  C.bar = (uint64_t*)(base + L.bar);
 
   const int Nc = (int)(P.comp_ptr[c + 1] - P.comp_ptr[c]);
   C.Nc = Nc;
@@ -522,9 +527,12 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
       nu *= 2.0;
     }
   }
-  for (int i = tid; i < C.n; i += T) {
-    const int l = C.lof[i >> 1];
-    P.positions[2 * (size_t)C.node[l] + (i & 1)] = C.x[2 * l + (i & 1)];
+  // (not after FAILURE: Ceres only commits a usable solution, solver.cc Minimize / IsSolutionUsable)
+  if (term != LFR_TERM_FAILURE) {
+    for (int i = tid; i < C.n; i += T) {
+      const int l = C.lof[i >> 1];
+      P.positions_out[2 * (size_t)C.node[l] + (i & 1)] = C.x[2 * l + (i & 1)];
+    }
   }
   if (tid == 0) {
     P.st_iter[c] = iter;

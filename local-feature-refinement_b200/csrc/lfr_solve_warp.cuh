@@ -32,7 +32,11 @@ struct DevProblem {
   const uint32_t* comp_ptr;
   const uint32_t* comp_nodes;
   const uint32_t* local_of;  // node -> index inside its component's node list
-  double* positions;         // [2N] in/out
+  double* positions;         // [2N] start point (device memory)
+  double* positions_out;     // [2N] results: `positions` itself, or the caller's pinned host buffer
+                             // (zero-copy write-back: only free nodes are written, solve.cc:131-141)
+  int stage_mode;            // how the staging tiers pull a component's edge records into shared memory:
+                             // 1 = TMA 1-D bulk copies (cp.async.bulk + mbarrier), 0 = LDG -> STS
   // per dispatch slot
   int32_t* st_iter;
   int32_t* st_term;
@@ -601,9 +605,12 @@ solve_warp_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     }
   }
   // ---- write back the last accepted x ---------------------------------------------------
-  for (int i = lane; i < C.n; i += 32) {
-    const int l = C.lof[i >> 1];
-    P.positions[2 * (size_t)C.node[l] + (i & 1)] = C.x[2 * l + (i & 1)];
+  // (not after FAILURE: Ceres only commits a usable solution, solver.cc Minimize / IsSolutionUsable)
+  if (term != LFR_TERM_FAILURE) {
+    for (int i = lane; i < C.n; i += 32) {
+      const int l = C.lof[i >> 1];
+      P.positions_out[2 * (size_t)C.node[l] + (i & 1)] = C.x[2 * l + (i & 1)];
+    }
   }
   if (lane == 0) {
     P.st_iter[c] = iter;

@@ -27,6 +27,7 @@
 namespace lfr {
 
 struct Warp2Layout {
+  int stage, bar;                                   // staged 80-byte edge records (float4 x 5 each), mbarrier
   int x, xc, g, S, dl, H, scr, tup, prow;           // doubles (byte offsets)
   int eidx, meta, node, rowstart, candptr, cnt;     // u32 / i32
   int twin, outptr, freeof, lof;                    // u16 / i16
@@ -34,6 +35,8 @@ struct Warp2Layout {
   __host__ __device__ Warp2Layout(int emax, int ncmax, int n2max) {
     ldh = n2max | 1;  // odd row stride (in doubles): lanes reading one column hit distinct banks
     int o = 0;
+    stage = o; o += 80 * emax;  // 16-byte aligned: destination of the bulk copies
+    bar = o; o += 16;
     x = o; o += 16 * ncmax;
     xc = o; o += 16 * ncmax;
     g = o; o += 8 * n2max;
@@ -66,8 +69,47 @@ struct Warp2Ctx {
   uint32_t *eidx, *meta, *node;
   uint16_t *twin, *outptr, *lof;
   int16_t* freeof;
-  const float4* edges;
+  float4* stage;   // this component's candidate out-edge records in shared memory, 5 x float4 each
+  uint64_t* bar;   // mbarrier the bulk copies complete on
 };
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (sm_90+; here sm_100a) -------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+template <int N>
+__device__ __forceinline__ void warp_sum_n(double (&v)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double t[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) t[k] = __shfl_xor_sync(kFull, v[k], o);
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] += t[k];
+  }
+}
 
 __device__ __forceinline__ void warp_sum2_max1(double& s0, double& s1, double& m0) {
 #pragma unroll
@@ -88,22 +130,31 @@ __device__ __forceinline__ void warp_sum2(double& s0, double& s1) {
   }
 }
 
-// Same staging as eval_pass (lfr_solve_warp.cuh) for the v2 context.
+// Lane partials of |x - xc|^2 and |xc|^2 over the free coordinates, produced where the candidate
+// is formed (make_candidate2) and summed in the evaluation pass's butterfly: the parameter-tolerance
+// test and the accepted point's norm cost no reduction of their own.
+struct CandNorms {
+  double dn2, xn2;
+};
+
+// Evaluate every kept edge at positions `xe` ([2*Nc], component-local) from the records staged in
+// shared memory (five conflict-free LDS.128 per edge: 80-byte stride = 20 banks, a quarter-warp of
+// 16-byte accesses covers all 32 banks once); stage {a, r, M} (7 doubles, SoA) for the assembly.
 // DIRDERIV = true additionally returns phi'(alpha) = grad f(xe) . dl of the line
 // search, accumulated per edge from the same evaluation:
 //   grad . dl = sum_e a_e r_e^T (dl_dst - M_e dl_src)      (J_src = -M, J_dst = I)
 // so a line-search trial needs no separate gradient assembly pass.
-template <bool DIRDERIV>
+template <bool DIRDERIV, bool NORMS>
 __device__ __forceinline__ double eval_pass2(const Warp2Ctx& C, const double* xe, const DevConsts& K,
-                                             double* dphi = nullptr) {
+                                             double* dphi = nullptr, CandNorms* nrm = nullptr) {
   double cost = 0.0, dd = 0.0;
   for (int j = C.lane; j < C.Ec; j += 32) {
     const uint32_t mt = C.meta[j];
     const int s = mt & 0xfff, d = (mt >> 12) & 0xfff, kind = mt >> 24;
-    const float4* qp = C.edges + 5 * (size_t)C.eidx[j];
+    const float4* qp = C.stage + 5 * C.eidx[j];
     float4 q[5];
 #pragma unroll
-    for (int t = 0; t < 5; ++t) q[t] = __ldg(qp + t);
+    for (int t = 0; t < 5; ++t) q[t] = qp[t];
     const EdgeEval ev = eval_edge(q, kind, xe[2 * s], xe[2 * s + 1], xe[2 * d], xe[2 * d + 1], K);
     double* sc = C.scr + j;
     sc[0] = ev.a;
@@ -121,7 +172,20 @@ __device__ __forceinline__ double eval_pass2(const Warp2Ctx& C, const double* xe
       dd += ev.a * (ev.r0 * (d0 - (ev.m00 * s0 + ev.m01 * s1)) + ev.r1 * (d1 - (ev.m10 * s0 + ev.m11 * s1)));
     }
   }
-  if (DIRDERIV) {
+  if (DIRDERIV && NORMS) {
+    double v[4] = {cost, dd, nrm->dn2, nrm->xn2};
+    warp_sum_n<4>(v);
+    cost = v[0];
+    *dphi = v[1];
+    nrm->dn2 = v[2];
+    nrm->xn2 = v[3];
+  } else if (NORMS) {
+    double v[3] = {cost, nrm->dn2, nrm->xn2};
+    warp_sum_n<3>(v);
+    cost = v[0];
+    nrm->dn2 = v[1];
+    nrm->xn2 = v[2];
+  } else if (DIRDERIV) {
     warp_sum2(cost, dd);
     *dphi = dd;
   } else {
@@ -389,14 +453,22 @@ __device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const
   return ok && finite;
 }
 
-__device__ __forceinline__ void make_candidate2(const Warp2Ctx& C, double alpha, const DevConsts& K) {
+__device__ __forceinline__ CandNorms make_candidate2(const Warp2Ctx& C, double alpha, const DevConsts& K) {
+  CandNorms nr{0.0, 0.0};
   for (int i = C.lane; i < 2 * C.Nc; i += 32) {
     const int f = C.freeof[i >> 1];
-    double v = C.x[i];
-    if (f >= 0) v = fmin(fmax(v + alpha * C.dl[2 * f + (i & 1)], -K.bound), K.bound);
+    const double xv = C.x[i];
+    double v = xv;
+    if (f >= 0) {
+      v = fmin(fmax(xv + alpha * C.dl[2 * f + (i & 1)], -K.bound), K.bound);
+      const double dv = xv - v;
+      nr.dn2 += dv * dv;
+      nr.xn2 += v * v;
+    }
     C.xc[i] = v;
   }
   __syncwarp();
+  return nr;
 }
 
 // Component setup by ONE warp (solve.cc:98-143): node list and start point,
@@ -404,6 +476,52 @@ __device__ __forceinline__ void make_candidate2(const Warp2Ctx& C, double alpha,
 // Tukey, other component or root-root -> dropped) with ballots, out-edge ranges,
 // free-variable numbering, and the twin (reverse edge) of every kept edge.
 // Shared by the warp kernel and the tile kernel (whose warp 0 runs it).
+// Pull the candidate out-edge records of every node of the component into shared memory, once:
+// a node's out-edges are contiguous in the CSR array, so each node is ONE 1-D bulk copy
+// (cp.async.bulk, 80 * degree bytes, 16-byte aligned on both sides) completing on the warp's
+// mbarrier; all copies are in flight together and no register is tied up.  `P.edges` may be device
+// memory or the caller's pinned host buffer (zero-copy over PCIe: the records are read exactly
+// once either way, every later evaluation runs from shared memory).
+template <class Ctx>
+__device__ __forceinline__ void stage_edges(Ctx& C, const uint32_t* rowstart, const uint32_t* candptr, int Nc,
+                                            int Eup, const DevProblem& P, int lane) {
+  if (Eup == 0) return;
+  if (P.stage_mode == 1) {
+    if (lane == 0) mbar_arrive_expect_tx(C.bar, 80u * (uint32_t)Eup);
+    __syncwarp();
+    for (int l = lane; l < Nc; l += 32) {
+      const uint32_t d = candptr[l + 1] - candptr[l];
+      if (d) bulk_copy_g2s(C.stage + 5 * candptr[l], P.edges + 5 * (size_t)rowstart[l], 80u * d, C.bar);
+    }
+    mbar_wait(C.bar, 0);
+  } else {
+    // LDG -> STS, lane-linear over the 16-byte words, four loads in flight per lane
+    const int W = 5 * Eup;
+    for (int w0 = lane; w0 < W; w0 += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int w = w0 + 32 * u;
+        if (w < W) {
+          const int k = w / 5, t = w - 5 * k;
+          int lo = 0, hi = Nc - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int)candptr[mid] <= k) lo = mid; else hi = mid - 1;
+          }
+          v[u] = __ldg(P.edges + 5 * (size_t)(rowstart[lo] + (uint32_t)(k - (int)candptr[lo])) + t);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int w = w0 + 32 * u;
+        if (w < W) C.stage[w] = v[u];
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <class Ctx>
 __device__ __forceinline__ void warp_setup(Ctx& C, uint32_t* rowstart, uint32_t* candptr, int* cnt, int ncmax,
                                            const DevProblem& P, const DevConsts& K, uint32_t c, int lane,
@@ -411,6 +529,7 @@ __device__ __forceinline__ void warp_setup(Ctx& C, uint32_t* rowstart, uint32_t*
   const uint32_t nbeg = P.comp_ptr[c];
   const int Nc = (int)(P.comp_ptr[c + 1] - nbeg);
   C.Nc = Nc;
+  if (P.stage_mode == 1 && lane == 0) mbar_init(C.bar, 1);
   int run = 0;
   for (int l0 = 0; l0 < Nc; l0 += 32) {
     const int l = l0 + lane;
@@ -438,6 +557,7 @@ __device__ __forceinline__ void warp_setup(Ctx& C, uint32_t* rowstart, uint32_t*
   if (lane == 0) candptr[Nc] = run;
   __syncwarp();
   const int Eup = run;
+  stage_edges(C, rowstart, candptr, Nc, Eup, P, lane);
   int kept = 0;
   for (int k0 = 0; k0 < Eup; k0 += 32) {
     const int k = k0 + lane;
@@ -449,9 +569,9 @@ __device__ __forceinline__ void warp_setup(Ctx& C, uint32_t* rowstart, uint32_t*
         const int mid = (lo + hi + 1) >> 1;
         if ((int)candptr[mid] <= k) lo = mid; else hi = mid - 1;
       }
-      e = rowstart[lo] + (uint32_t)(k - (int)candptr[lo]);
+      e = (uint32_t)k;  // index of the record in the staged array
       const uint32_t v = C.node[lo];
-      const uint32_t dst = __float_as_uint(__ldg(&P.edges[5 * (size_t)e + 4].w));
+      const uint32_t dst = __float_as_uint(C.stage[5 * k + 4].w);
       if (dst >= P.n_nodes || dst == v) {
         *P.err_flag = 1;  // malformed input: reported by the host as LFR_EINVAL
       } else {
@@ -527,6 +647,8 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   C.lane = lane;
   C.emax = B.emax;
   C.ldh = L.ldh;
+  C.stage = (float4*)(base + L.stage);
+  C.bar = (uint64_t*)(base + L.bar);
   C.x = (double*)(base + L.x);
   C.xc = (double*)(base + L.xc);
   C.g = (double*)(base + L.g);
@@ -547,7 +669,6 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   C.outptr = (uint16_t*)(base + L.outptr);
   C.freeof = (int16_t*)(base + L.freeof);
   C.lof = (uint16_t*)(base + L.lof);
-  C.edges = P.edges;
 
   const bool prof = (P.st_cycles != nullptr);
   long long t_begin = prof ? clock64() : 0, t_mark = t_begin;
@@ -580,7 +701,7 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   LFR_TICK(cyc_setup);
 
   // ---- iteration 0 -----------------------------------------------------------------
-  double cost = eval_pass2<false>(C, C.x, K);
+  double cost = eval_pass2<false, false>(C, C.x, K);
   LFR_TICK(cyc_eval);
   double gmax = assemble2<false>(C, true, K);
   LFR_TICK(cyc_asm);
@@ -589,20 +710,6 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   int iter = 0, n_invalid = 0, term = LFR_TERM_NO_CONVERGENCE;
   unsigned ls_steps = 0;
   bool success = true;
-  // |x|^2 and |x - xc|^2 over the free coordinates in one butterfly
-  auto norms = [&](double* xn2, double* dn2) {
-    double a = 0.0, b = 0.0;
-    for (int i = lane; i < C.n; i += 32) {
-      const int l = C.lof[i >> 1];
-      const double xv = C.x[2 * l + (i & 1)], dv = xv - C.xc[2 * l + (i & 1)];
-      a += xv * xv;
-      b += dv * dv;
-    }
-    warp_sum2(a, b);
-    __syncwarp();  // the reads of x above are ordered before the accept step's writes (the shuffles are not a memory barrier)
-    *xn2 = a;
-    *dn2 = b;
-  };
   double x_norm;
   {
     double a = 0.0;
@@ -634,8 +741,8 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     }
     n_invalid = 0;
     // projected Armijo line search along dl (bounds-constrained problem, A.7b)
-    make_candidate2(C, 1.0, K);
-    double cost_c = eval_pass2<false>(C, C.xc, K);
+    CandNorms nr = make_candidate2(C, 1.0, K);
+    double cost_c = eval_pass2<false, true>(C, C.xc, K, nullptr, &nr);
     LFR_TICK(cyc_eval);
     bool c_valid = isfinite(cost_c);
     if (!c_valid || cost_c > cost + K.ls_suff * gd * 1.0) {
@@ -657,9 +764,9 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
         LFR_TICK(cyc_poly);
         if (step * dmax < K.ls_min_step) break;
         previous = current;
-        make_candidate2(C, step, K);
+        nr = make_candidate2(C, step, K);
         double dphi;
-        cost_c = eval_pass2<true>(C, C.xc, K, &dphi);
+        cost_c = eval_pass2<true, true>(C, C.xc, K, &dphi, &nr);
         c_valid = isfinite(cost_c);
         current = LsSample{step, cost_c, 0.0, c_valid, false};
         if (c_valid) {
@@ -672,30 +779,23 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
         for (int i = lane; i < C.n; i += 32) C.dl[i] *= current.x;
         __syncwarp();
       } else {  // line search failed: delta unchanged, candidate = P(x + delta)
-        make_candidate2(C, 1.0, K);
-        cost_c = eval_pass2<false>(C, C.xc, K);
+        nr = make_candidate2(C, 1.0, K);
+        cost_c = eval_pass2<false, true>(C, C.xc, K, nullptr, &nr);
         c_valid = isfinite(cost_c);
       }
     }
     if (!c_valid) cost_c = 1.7976931348623157e308;
-    double xn2, dn2;
-    norms(&xn2, &dn2);
-    const double step_norm = sqrt(dn2);
+    const double step_norm = sqrt(nr.dn2);
     if (step_norm <= K.p_tol * (x_norm + K.p_tol)) { term = LFR_TERM_PARAMETER_TOL; break; }
     if (fabs(cost - cost_c) <= K.f_tol * cost) { term = LFR_TERM_FUNCTION_TOL; break; }
     const double rho = (cost - cost_c) / model_change;
     if (rho > K.min_rel_decrease) {
-      double a2 = 0.0;
-      for (int i = lane; i < 2 * Nc; i += 32) {
-        const double v = C.xc[i];
-        C.x[i] = v;
-        if (C.freeof[i >> 1] >= 0) a2 += v * v;
-      }
+      for (int i = lane; i < 2 * Nc; i += 32) C.x[i] = C.xc[i];
       __syncwarp();
       cost = cost_c;
       LFR_TICK(cyc_ls);
       gmax = assemble2<false>(C, false, K);
-      x_norm = sqrt(warp_sum(a2));
+      x_norm = sqrt(nr.xn2);
       LFR_TICK(cyc_asm);
       success = true;
       const double t = 2.0 * rho - 1.0;
@@ -707,9 +807,12 @@ solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     }
   }
   // ---- write back the last accepted x ---------------------------------------------------
-  for (int i = lane; i < C.n; i += 32) {
-    const int l = C.lof[i >> 1];
-    P.positions[2 * (size_t)C.node[l] + (i & 1)] = C.x[2 * l + (i & 1)];
+  // (not after FAILURE: Ceres only commits a usable solution, solver.cc Minimize / IsSolutionUsable)
+  if (term != LFR_TERM_FAILURE) {
+    for (int i = lane; i < C.n; i += 32) {
+      const int l = C.lof[i >> 1];
+      P.positions_out[2 * (size_t)C.node[l] + (i & 1)] = C.x[2 * l + (i & 1)];
+    }
   }
   if (lane == 0) {
     P.st_iter[c] = iter;

@@ -113,18 +113,58 @@ def test_duplicate_pairs_take_the_serial_assembly_path(b200, oracle):
     assert np.array_equal(st_g["iterations"], st_o["iterations"])
 
 
-@pytest.mark.parametrize("env,cfg", [("LFR_FORCE_V1", "cfg1"), ("LFR_FORCE_V1", "cfg3"), ("LFR_NO_TILE", "cfg4"),
-                                     ("LFR_TILE_FROM_N", "cfg2")])
-def test_fallback_tiers_match_oracle(b200, oracle, monkeypatch, env, cfg):
+def _compare_dbg(b200, oracle, p, debug_flags, **opts):
+    """_compare with lfr_options.debug_flags set on the GPU side only (the oracle ignores them)."""
+    pos_g, st_g = b200.solve(p, b200.default_options(debug_flags=debug_flags, **opts))
+    pos_o, st_o = oracle.solve(p, oracle.default_options(n_threads=8, **opts))
+    assert np.abs(pos_g - pos_o).max() <= TOL_UNITS
+    np.testing.assert_array_equal(st_g["termination"], st_o["termination"])
+    np.testing.assert_array_equal(st_g["iterations"], st_o["iterations"])
+    return pos_g, st_g
+
+
+@pytest.mark.parametrize("flags,cfg", [("FORCE_SMEM_CHOLESKY", "cfg1"), ("FORCE_SMEM_CHOLESKY", "cfg3"),
+                                       ("NO_TILE", "cfg4"), ("TILE_FROM_1", "cfg2")])
+def test_fallback_tiers_match_oracle(b200, oracle, flags, cfg):
     """The shared-memory Cholesky warp kernel (solve_warp_kernel) is the tier for
-    80 < n <= 96 unknowns and the fallback behind the register kernels; the
-    schedule reads LFR_FORCE_V1 / LFR_NO_TILE per plan, so the same scenes can be
-    sent through it (cfg4 without the tile tier: v1 for 32 < n <= 96).  LFR_TILE_FROM_N=1
-    routes every component with n <= 32 to the two-warp tile kernel <64, 32> instead of the
-    one-warp kernel."""
-    monkeypatch.setenv(env, "1")
+    80 < n <= 96 unknowns and the fallback behind the register kernels; lfr_options.debug_flags
+    (LFR_DBG_*) route the same scenes through it (cfg4 without the tile tier: v1 for
+    32 < n <= 96).  TILE_FROM = 1 routes every component with n <= 32 to the two-warp tile
+    kernel <64, 32> instead of the one-warp kernel."""
+    from lfr_b200 import capi
+    dbg = {"FORCE_SMEM_CHOLESKY": capi.DBG_FORCE_SMEM_CHOLESKY, "NO_TILE": capi.DBG_NO_TILE,
+           "TILE_FROM_1": 1 << capi.DBG_TILE_FROM_SHIFT}[flags]
     _, p = get_problem(cfg)
-    _compare(b200, oracle, p)
+    _compare_dbg(b200, oracle, p, dbg)
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg4"])
+def test_staging_and_zero_copy_variants_are_bitwise_identical(b200, oracle, cfg):
+    """The same solve with (a) TMA bulk staging from the caller's pinned buffers (zero-copy: edge
+    records pulled over PCIe straight into shared memory, results written straight back), (b) the
+    same through HBM, (c) LDG -> STS staging: identical bits, all equal to the oracle to 1e-4 px."""
+    import ctypes as C
+    import torch
+    from lfr_b200 import capi
+    _, p = get_problem(cfg)
+    pos_ref, st_ref = _compare_dbg(b200, oracle, p, capi.DBG_NO_ZERO_COPY)
+    pos_ldg, st_ldg = b200.solve(p, b200.default_options(debug_flags=capi.DBG_NO_ZERO_COPY | capi.DBG_STAGE_LDG))
+    assert np.array_equal(pos_ref, pos_ldg) and np.array_equal(st_ref["iterations"], st_ldg["iterations"])
+    # pinned caller buffers -> zero-copy
+    s, keep = b200.marshal(p)
+    e_pin = torch.empty(keep["edges"].nbytes, dtype=torch.uint8).pin_memory()
+    e_pin.numpy()[:] = keep["edges"].view(np.uint8).reshape(-1)
+    s.edges = e_pin.data_ptr()
+    N = p.graph.n_nodes
+    for dbg in (0, capi.DBG_STAGE_LDG):
+        pos_pin = torch.zeros(2 * N, dtype=torch.float64).pin_memory()
+        st, bufs = b200.make_stats(p.n_components)
+        o = b200.default_options(debug_flags=dbg)
+        rc = b200.lib.lfr_solve(C.byref(s), C.byref(o), C.c_void_p(pos_pin.data_ptr()), C.byref(st))
+        b200.check(rc, "lfr_solve")
+        assert np.array_equal(pos_pin.numpy().reshape(N, 2), pos_ref), dbg
+        assert np.array_equal(bufs["iterations"], st_ref["iterations"])
+        assert np.array_equal(bufs["termination"], st_ref["termination"])
 
 
 def _quartic_cases(rng, n):

@@ -2,7 +2,6 @@
 import os
 import sys
 
-os.environ["LFR_PROFILE"] = "1"
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
 import ctypes as C  # noqa: E402
@@ -15,7 +14,7 @@ from lfr_b200.capi import Plan, load_b200  # noqa: E402
 lib = load_b200()
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 p = build_problem(synth.generate(cfg))
-plan = Plan(lib, p)
+plan = Plan(lib, p, lib.default_options(debug_flags=0x10))  # LFR_DBG_PROFILE
 import torch  # noqa: E402
 
 for _ in range(3):

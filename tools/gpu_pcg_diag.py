@@ -1,5 +1,4 @@
 import os, sys
-os.environ["LFR_PROFILE"] = "1"
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import ctypes as C
 import numpy as np
@@ -8,7 +7,7 @@ from lfr_b200 import build_problem, synth
 from lfr_b200.capi import Plan, load_b200
 lib = load_b200(); orc = load_oracle()
 p = build_problem(synth.generate(sys.argv[1] if len(sys.argv) > 1 else "ring200"))
-plan = Plan(lib, p); plan.solve(); pos_g, st_g = plan.download()
+plan = Plan(lib, p, lib.default_options(debug_flags=0x10))  # LFR_DBG_PROFILE; plan.solve(); pos_g, st_g = plan.download()
 cyc = np.zeros((p.n_components, 8), dtype=np.uint64)
 lib.lib.lfr_debug_plan_cycles.argtypes = [C.c_void_p, C.c_void_p]
 lib.lib.lfr_debug_plan_cycles(plan.handle, cyc.ctypes.data)

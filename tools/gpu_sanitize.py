@@ -33,12 +33,10 @@ for w in which:
         ms = synth.generate("cfg1")
         opts = lib.default_options(linear_solver=2)
     elif w == "v1":
-        os.environ["LFR_FORCE_V1"] = "1"
         ms = synth.generate("cfg1")
-        opts = lib.default_options()
+        opts = lib.default_options(debug_flags=1)  # LFR_DBG_FORCE_SMEM_CHOLESKY
     p = build_problem(ms)
     pos, st = lib.solve(p, opts)
-    os.environ.pop("LFR_FORCE_V1", None)
     sizes = np.diff(p.comp_ptr.astype(np.int64))
     print(w, "components", p.n_components, "max nodes", int(sizes.max()) if sizes.size else 0,
           "iterations", int(st["total_iterations"]), "finite", bool(np.isfinite(pos).all()))
