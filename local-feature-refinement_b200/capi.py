@@ -17,6 +17,7 @@ from .graph import EDGE_DTYPE, Problem
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 B200_LIB_PATH = os.path.join(HERE, "csrc", "liblfr_b200.so")
+HOST_LIB_PATH = os.path.join(HERE, "csrc", "liblfr_host.so")
 
 LFR_OK = 0
 # lfr_options.debug_flags (include/lfr.h)
@@ -259,3 +260,17 @@ def load_b200() -> Library:
         if _b200.backend != "b200":
             raise RuntimeError("lfr: %s is not the b200 backend" % B200_LIB_PATH)
     return _b200
+
+
+_host: Optional[C.CDLL] = None
+
+
+def load_host() -> C.CDLL:
+    """The CPU-only host utilities (csrc/liblfr_host.so: protobuf wire codec, include/lfr_wire.h, and the
+    host graph stage, include/lfr_host.h).  No CUDA dependency."""
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError("lfr: %s is missing — build it first (python __graft_entry__.py build)" % HOST_LIB_PATH)
+        _host = C.CDLL(HOST_LIB_PATH)
+    return _host

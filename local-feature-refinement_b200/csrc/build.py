@@ -1,34 +1,56 @@
-"""Build csrc/liblfr_b200.so in-tree with nvcc for sm_100a (cross-compiles
-without a GPU).  The .so is git-ignored but travels to the GPU box."""
+"""Build the in-tree libraries (git-ignored, but they travel to the GPU box):
+
+  liblfr_b200.so  the product: CUDA kernels + the C ABI of include/lfr.h      (nvcc, sm_100a; cross-compiles without a GPU)
+  liblfr_host.so  CPU-only host utilities behind include/lfr_wire.h and include/lfr_host.h
+                  (protobuf wire codec, host graph stage) — no CUDA dependency, so the
+                  reference arm of bench.py and the tests can use them without mapping the product library
+"""
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "liblfr_b200.so")
-SOURCES = ["lfr_capi.cu", "lfr_wire.cc", "lfr_host.cc"]
-DEPS = SOURCES + ["lfr_solve_warp.cuh", "lfr_solve_warp2.cuh", "lfr_solve_cta.cuh", "lfr_solve_tile.cuh", "lfr_math.cuh", os.path.join("..", "..", "include", "lfr.h"),
-                  os.path.join("..", "..", "include", "lfr_wire.h"),
-                  os.path.join("..", "..", "include", "lfr_host.h")]
+OUT_HOST = os.path.join(HERE, "liblfr_host.so")
+SOURCES = ["lfr_capi.cu"]
+HOST_SOURCES = ["lfr_wire.cc", "lfr_host.cc"]
+INC = os.path.join("..", "..", "include")
+DEPS = SOURCES + ["lfr_solve_warp.cuh", "lfr_solve_warp2.cuh", "lfr_solve_cta.cuh", "lfr_solve_tile.cuh", "lfr_math.cuh",
+                  os.path.join(INC, "lfr.h")]
+HOST_DEPS = HOST_SOURCES + ["lfr_cut.h", os.path.join(INC, "lfr.h"), os.path.join(INC, "lfr_wire.h"),
+                            os.path.join(INC, "lfr_host.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
 
 
 def build_variant(out: str, defines) -> str:
     """Diagnostic variant of the library (e.g. -DLFR_POLY_PROF) next to the product .so."""
-    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"] + ["-D" + d for d in defines] + \
-          ["-o", os.path.join(HERE, out)] + [os.path.join(HERE, s) for s in SOURCES]
+    cmd = [NVCC] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", os.path.join(HERE, out)] + \
+          [os.path.join(HERE, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return os.path.join(HERE, out)
 
 
+def _stale(out, deps):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in deps)
+
+
+def build_host(force: bool = False) -> str:
+    if force or _stale(OUT_HOST, HOST_DEPS):
+        subprocess.check_call(["g++", "-std=c++17", "-O3", "-fPIC", "-shared", "-Wall", "-o", OUT_HOST] +
+                              [os.path.join(HERE, s) for s in HOST_SOURCES])
+    return OUT_HOST
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    newest = max(os.path.getmtime(os.path.join(HERE, d)) for d in DEPS)
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
+    build_host(force)
+    if not force and not _stale(OUT, DEPS):
         return OUT
-    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
-           "-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+    cmd = [NVCC] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

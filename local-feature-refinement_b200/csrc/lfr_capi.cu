@@ -135,7 +135,7 @@ struct lfr_plan {
   uint32_t N = 0, C = 0;
   uint64_t E = 0;
   uint32_t total_slots = 0;
-  DevBuf row_ptr, edges, track, comp, is_root, comp_ptr, comp_nodes, local_of, pos, pos_init, stats, cycles, lists;
+  DevBuf row_ptr, edges, track, comp, is_root, comp_ptr, comp_nodes, local_of, pos, pos_init, stats, cycles, times, lists;
   // `stats` is one block (one memset, one D2H copy): cost0[Cp] cost1[Cp] iter[Cp] term[Cp] ls[Cp] kept[Cp] err[2]
   uint32_t Cp = 0;               // C rounded up to an even count
   bool pos_is_staged = false;    // lfr_solve(): the start point was uploaded straight into `pos`
@@ -192,6 +192,7 @@ struct lfr_plan {
     P.st_ls = d_ls();
     P.st_kept = d_kept();
     P.st_cycles = profile ? cycles.as<unsigned long long>() : nullptr;
+    P.st_times = profile ? times.as<unsigned long long>() : nullptr;
     P.err_flag = d_err();
     return P;
   }
@@ -202,7 +203,7 @@ namespace {
 void free_plan(lfr_plan* pl) {
   if (!pl) return;
   DevBuf* bufs[] = {&pl->row_ptr, &pl->edges, &pl->track, &pl->comp, &pl->is_root, &pl->comp_ptr, &pl->comp_nodes,
-                    &pl->local_of, &pl->pos, &pl->pos_init, &pl->stats, &pl->cycles, &pl->lists, &pl->L_comps, &pl->L_eidx, &pl->L_meta,
+                    &pl->local_of, &pl->pos, &pl->pos_init, &pl->stats, &pl->cycles, &pl->times, &pl->lists, &pl->L_comps, &pl->L_eidx, &pl->L_meta,
                     &pl->L_inlist, &pl->L_twin, &pl->L_fdst, &pl->L_bmat, &pl->L_scr, &pl->L_q, &pl->L_node, &pl->L_outptr, &pl->L_inptr, &pl->L_freeof,
                     &pl->L_x, &pl->L_xc, &pl->L_lof, &pl->L_vec};
   for (DevBuf* b : bufs) b->release();
@@ -503,7 +504,12 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
   LFR_TRY(pl->pos.reserve(sizeof(double) * 2 * N));
   pl->Cp = (uint32_t)((C + 1) & ~(size_t)1);
   LFR_TRY(pl->stats.reserve(pl->stats_bytes()));
-  if (pl->profile) LFR_TRY(pl->cycles.reserve(sizeof(unsigned long long) * 8 * C));
+  if (pl->profile) {
+    LFR_TRY(pl->cycles.reserve(sizeof(unsigned long long) * 8 * C));
+    LFR_TRY(pl->times.reserve(sizeof(unsigned long long) * 2 * C));
+    LFR_CUDA(cudaMemsetAsync(pl->cycles.p, 0, sizeof(unsigned long long) * 8 * C, s));
+    LFR_CUDA(cudaMemsetAsync(pl->times.p, 0, sizeof(unsigned long long) * 2 * C, s));
+  }
   // per-slot stats default to "skipped" (size-1 components never run); also clears the error flag
   LFR_CUDA(cudaMemsetAsync(pl->stats.p, 0, pl->stats_bytes(), s));
   if (stage_positions_directly) {
@@ -844,6 +850,18 @@ int lfr_debug_plan_cycles(lfr_plan* pl, unsigned long long* out) {
   if (!pl || !pl->profile) return fail(LFR_EINVAL, "plan was not created with LFR_PROFILE=1");
   LFR_CUDA(cudaSetDevice(pl->device));
   LFR_CUDA(cudaMemcpy(out, pl->cycles.p, sizeof(unsigned long long) * 8 * (size_t)pl->C, cudaMemcpyDeviceToHost));
+  return LFR_OK;
+}
+
+/* debug (LFR_DBG_PROFILE): counters of the last lfr_solve() of this thread on `device`:
+   cycles [8 per slot], times [2 per slot] = %globaltimer ns at start / end of each component */
+int lfr_debug_last_solve_profile(int device, unsigned long long* cycles, unsigned long long* times) {
+  if (device < 0 || device >= kMaxDevices || !g_ws[device].ready || !g_ws[device].plan->profile)
+    return fail(LFR_EINVAL, "no profiled lfr_solve() on this device / thread");
+  lfr_plan* pl = g_ws[device].plan;
+  LFR_CUDA(cudaSetDevice(device));
+  if (cycles) LFR_CUDA(cudaMemcpy(cycles, pl->cycles.p, sizeof(unsigned long long) * 8 * (size_t)pl->C, cudaMemcpyDeviceToHost));
+  if (times) LFR_CUDA(cudaMemcpy(times, pl->times.p, sizeof(unsigned long long) * 2 * (size_t)pl->C, cudaMemcpyDeviceToHost));
   return LFR_OK;
 }
 

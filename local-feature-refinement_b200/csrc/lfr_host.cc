@@ -5,6 +5,7 @@
 // tested to produce identical arrays.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "../../include/lfr_host.h"
+#include "lfr_cut.h"
 
 struct lfr_host_stage {
   uint32_t N = 0, T = 0, C = 0;
@@ -25,6 +27,81 @@ namespace {
 
 using Clock = std::chrono::steady_clock;
 double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
+
+// ---- open-addressing hash map uint64 -> uint32 (linear probing, power-of-two capacity) -------
+// The reference interns nodes through std::map<pair<string, size_t>> (solve.cc:53-65) and meta
+// edges through unordered_map (solve.cc:268-289); only the mapping matters, not the container.
+struct FlatMap {
+  std::vector<uint64_t> keys;
+  std::vector<uint32_t> vals;
+  uint64_t mask = 0;
+  static constexpr uint64_t kEmpty = ~0ull;
+  explicit FlatMap(size_t expected) {
+    size_t cap = 16;
+    while (cap < expected * 2 + 16) cap <<= 1;
+    keys.assign(cap, kEmpty);
+    vals.assign(cap, 0);
+    mask = cap - 1;
+  }
+  static uint64_t mix(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    return x;
+  }
+  // returns the slot of `key`; *fresh = true when it was just inserted (caller sets vals[slot])
+  size_t find_or_insert(uint64_t key, bool* fresh) {
+    size_t i = (size_t)(mix(key) & mask);
+    for (;;) {
+      if (keys[i] == key) {
+        *fresh = false;
+        return i;
+      }
+      if (keys[i] == kEmpty) {
+        keys[i] = key;
+        *fresh = true;
+        return i;
+      }
+      i = (i + 1) & mask;
+    }
+  }
+};
+
+// float -> uint32 whose unsigned order is the float order (finite values)
+inline uint32_t sortable_bits(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Indices 0..M-1 sorted ASCENDING by (key[i], n1[i], n2[i]): LSD radix sort on the 32-bit key
+// (three 11-bit passes), then the rare runs of equal keys are ordered by (n1, n2).
+void sort_matches(const std::vector<uint32_t>& key, const std::vector<uint32_t>& n1, const std::vector<uint32_t>& n2,
+                  std::vector<uint32_t>* order_out) {
+  const size_t M = key.size();
+  std::vector<uint32_t> a(M), b(M);
+  std::iota(a.begin(), a.end(), 0u);
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = 11 * pass;
+    uint32_t hist[2049] = {0};
+    for (size_t i = 0; i < M; ++i) ++hist[((key[a[i]] >> shift) & 2047u) + 1];
+    for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
+    for (size_t i = 0; i < M; ++i) b[hist[(key[a[i]] >> shift) & 2047u]++] = a[i];
+    a.swap(b);
+  }
+  for (size_t i = 0; i < M;) {
+    size_t j = i + 1;
+    while (j < M && key[a[j]] == key[a[i]]) ++j;
+    if (j - i > 1)
+      std::sort(a.begin() + i, a.begin() + j, [&](uint32_t x, uint32_t y) {
+        if (n1[x] != n1[y]) return n1[x] < n1[y];
+        if (n2[x] != n2[y]) return n2[x] < n2[y];
+        return x < y;
+      });
+    i = j;
+  }
+  order_out->swap(a);
+}
 
 // ---- connected components, labelled in order of the lowest member index (solve.cc:291-300)
 std::vector<uint32_t> connected_components(uint32_t n, const std::vector<uint32_t>& a, const std::vector<uint32_t>& b,
@@ -54,142 +131,49 @@ std::vector<uint32_t> connected_components(uint32_t n, const std::vector<uint32_
   return label;
 }
 
-typedef std::map<uint32_t, std::map<uint32_t, int64_t>> Adj;
-
-std::vector<uint32_t> bfs_order(const Adj& adj, uint32_t start) {
-  std::vector<uint32_t> order(1, start);
-  std::map<uint32_t, bool> mark;
-  mark[start] = true;
-  for (size_t head = 0; head < order.size(); ++head) {
-    const uint32_t u = order[head];
-    for (const auto& kv : adj.at(u)) {  // std::map iterates neighbours in ascending order
-      if (!mark.count(kv.first)) {
-        mark[kv.first] = true;
-        order.push_back(kv.first);
-      }
-    }
-  }
-  return order;
-}
-
-// graph.py::two_way_cut — deterministic stand-in for ComputeNormalizedMinGraphCut(edges, weights, 2)
-std::map<uint32_t, int> two_way_cut(const Adj& adj, const std::vector<uint32_t>& node_weight) {
-  std::vector<uint32_t> nodes;
-  for (const auto& kv : adj) nodes.push_back(kv.first);  // ascending
-  std::map<uint32_t, bool> seen;
-  std::vector<std::vector<uint32_t>> pieces;
-  for (uint32_t s : nodes) {
-    if (seen.count(s)) continue;
-    std::vector<uint32_t> comp(1, s);
-    seen[s] = true;
-    for (size_t head = 0; head < comp.size(); ++head) {
-      const uint32_t u = comp[head];
-      for (const auto& kv : adj.at(u))
-        if (!seen.count(kv.first)) {
-          seen[kv.first] = true;
-          comp.push_back(kv.first);
-        }
-    }
-    pieces.push_back(comp);
-  }
-  std::map<uint32_t, int> out;
-  if (pieces.size() > 1) {
-    std::vector<std::pair<int64_t, size_t>> key(pieces.size());
-    for (size_t i = 0; i < pieces.size(); ++i) {
-      int64_t w = 0;
-      for (uint32_t x : pieces[i]) w += node_weight[x];
-      key[i] = std::make_pair(w, i);
-    }
-    std::stable_sort(key.begin(), key.end(), [&](const std::pair<int64_t, size_t>& p, const std::pair<int64_t, size_t>& q) {
-      if (p.first != q.first) return p.first > q.first;               // heaviest first
-      return pieces[p.second][0] < pieces[q.second][0];               // then by first node
-    });
-    int64_t w[2] = {0, 0};
-    for (const auto& k : key) {
-      const int side = (w[0] <= w[1]) ? 0 : 1;
-      w[side] += k.first;
-      for (uint32_t x : pieces[k.second]) out[x] = side;
-    }
-    return out;
-  }
-  const uint32_t start = bfs_order(adj, nodes[0]).back();
-  const std::vector<uint32_t> order = bfs_order(adj, start);
-  int64_t total = 0, acc = 0;
-  for (uint32_t x : nodes) total += node_weight[x];
-  for (size_t i = 0; i < order.size(); ++i) {
-    if (i > 0 && (acc * 2 >= total || i == order.size() - 1)) break;
-    out[order[i]] = 0;
-    acc += node_weight[order[i]];
-  }
-  for (uint32_t x : order)
-    if (!out.count(x)) out[x] = 1;
-  int cnt[2] = {0, 0};
-  for (const auto& kv : out) ++cnt[kv.second];
-  for (uint32_t x : order) {  // one refinement sweep
-    const int s = out[x];
-    if (cnt[s] <= 1) continue;
-    int64_t inside = 0, outside = 0;
-    for (const auto& kv : adj.at(x)) {
-      if (out[kv.first] == s) inside += kv.second; else outside += kv.second;
-    }
-    if (outside > inside) {
-      out[x] = 1 - s;
-      --cnt[s];
-      ++cnt[1 - s];
-    }
-  }
-  return out;
-}
-
-struct MetaEdge {
-  uint32_t a, b;
-  int64_t w;
-};
-
-// graph.py::recursive_cut (solve.cc:185-250 as a work list)
-void recursive_cut(const std::vector<MetaEdge>& edges0, const std::vector<uint32_t>& node_weight, uint32_t max_weight,
-                   std::vector<std::vector<uint32_t>>* groups) {
-  std::vector<std::vector<MetaEdge>> work(1, edges0);
+// graph.py::recursive_cut (solve.cc:185-250 as a work list): split until every group weighs
+// <= max_weight (node weight = nodes of the track, solve.cc:198) or has no internal edge (then its
+// nodes become singleton groups, solve.cc:240-246).  The 2-way cut itself is lfr_cut.h.
+void recursive_cut(std::vector<lfr::CutEdge> edges0, const std::vector<uint32_t>& node_weight, uint32_t max_weight,
+                   lfr::CutWorkspace& W, std::vector<std::vector<uint32_t>>* groups) {
+  std::vector<std::vector<lfr::CutEdge>> work;
+  work.push_back(std::move(edges0));
+  std::vector<uint8_t> covered;
   while (!work.empty()) {
-    std::vector<MetaEdge> edges = std::move(work.back());
+    const std::vector<lfr::CutEdge> edges = std::move(work.back());
     work.pop_back();
-    Adj adj;
-    for (const MetaEdge& e : edges) {
-      adj[e.a][e.b] += e.w;
-      adj[e.b][e.a] += e.w;
-    }
-    const std::map<uint32_t, int> side = two_way_cut(adj, node_weight);
+    lfr::two_way_cut(edges.data(), edges.size(), W);
+    const uint32_t n = (uint32_t)W.nodes.size();
+    std::vector<lfr::CutEdge> sub[2];
     for (int s = 0; s < 2; ++s) {
       std::vector<uint32_t> members;
       int64_t w = 0;
-      for (const auto& kv : side)
-        if (kv.second == s) {
-          members.push_back(kv.first);  // ascending
-          w += node_weight[kv.first];
+      for (uint32_t i = 0; i < n; ++i)
+        if (W.side[i] == s) {
+          members.push_back(W.nodes[i]);  // ascending
+          w += node_weight[W.nodes[i]];
         }
       if (members.empty()) continue;
       if (w <= (int64_t)max_weight) {
-        groups->push_back(members);  // solve.cc:205-211
+        groups->push_back(std::move(members));  // solve.cc:205-211
         continue;
       }
-      std::vector<MetaEdge> sub;
-      std::map<uint32_t, bool> covered;
-      for (const MetaEdge& e : edges) {
-        const auto ia = side.find(e.a), ib = side.find(e.b);
-        if (ia->second == s && ib->second == s) {
-          sub.push_back(e);
-          covered[e.a] = true;
-          covered[e.b] = true;
+      covered.assign(n, 0);
+      for (const lfr::CutEdge& e : edges) {
+        const int32_t la = W.local[e.a], lb = W.local[e.b];
+        if (W.side[la] == s && W.side[lb] == s) {
+          sub[s].push_back(e);
+          covered[la] = 1;
+          covered[lb] = 1;
         }
       }
-      if (!sub.empty()) {
-        work.push_back(sub);
-        for (uint32_t x : members)
-          if (!covered.count(x)) groups->push_back(std::vector<uint32_t>(1, x));
-      } else {
-        for (uint32_t x : members) groups->push_back(std::vector<uint32_t>(1, x));
-      }
+      for (uint32_t x : members)  // no edge left inside the subset: singleton groups
+        if (!covered[W.local[x]]) groups->push_back(std::vector<uint32_t>(1, x));
     }
+    lfr::cut_release(W);
+    // side 0 is processed before side 1 (the work list is a stack)
+    if (!sub[1].empty()) work.push_back(std::move(sub[1]));
+    if (!sub[0].empty()) work.push_back(std::move(sub[0]));
   }
 }
 
@@ -216,6 +200,10 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     seen_img[in->pair_img1[p]] = 1;
     seen_img[in->pair_img2[p]] = 1;
     for (uint64_t m = in->pair_ptr[p]; m < in->pair_ptr[p + 1]; ++m) {
+      if (!std::isfinite(in->sim[m])) {  // a NaN similarity has no place in the (sim, n1, n2) order of solve.cc:489
+        delete hs;
+        return LFR_EINVAL;
+      }
       kept_matches.push_back(m);
       m_img1.push_back(in->pair_img1[p]);
       m_img2.push_back(in->pair_img2[p]);
@@ -225,14 +213,14 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   const uint64_t M = kept_matches.size();
   std::vector<uint32_t> n1(M), n2(M);
   {
-    std::unordered_map<uint64_t, uint32_t> ids;
-    ids.reserve((size_t)(2 * M * 1.3) + 16);
+    FlatMap ids((size_t)(2 * M));
     auto intern = [&](uint32_t img, uint32_t feat) {
       const uint64_t key = ((uint64_t)img << 32) | feat;
-      auto it = ids.find(key);
-      if (it != ids.end()) return it->second;
+      bool fresh;
+      const size_t slot = ids.find_or_insert(key, &fresh);
+      if (!fresh) return ids.vals[slot];
       const uint32_t id = (uint32_t)hs->node_image.size();
-      ids.emplace(key, id);
+      ids.vals[slot] = id;
       hs->node_image.push_back(img);
       hs->node_feat.push_back(feat);
       return id;
@@ -275,21 +263,24 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   }
   const auto t_tracks = Clock::now();
   // ---- H2: constrained Kruskal (solve.cc:489-541) ------------------------------------------
-  std::vector<uint64_t> order(M);
-  std::iota(order.begin(), order.end(), (uint64_t)0);
-  std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) {  // sort + reverse on (sim, n1, n2)
-    const float sx = in->sim[kept_matches[x]], sy = in->sim[kept_matches[y]];
-    if (sx != sy) return sx > sy;
-    if (n1[x] != n1[y]) return n1[x] > n1[y];
-    if (n2[x] != n2[y]) return n2[x] > n2[y];
-    return x > y;
-  });
+  // std::sort + std::reverse on (sim, n1, n2) (solve.cc:489-490): ascending radix sort, walked backwards
+  std::vector<uint32_t> order;
+  {
+    std::vector<uint32_t> key(M);
+    for (uint64_t k = 0; k < M; ++k) key[k] = sortable_bits(in->sim[kept_matches[k]]);
+    sort_matches(key, n1, n2, &order);
+  }
   std::vector<int32_t> parent(N, -1);
-  std::vector<std::vector<uint16_t>> imgs(N);
-  for (uint32_t v = 0; v < N; ++v) imgs[v].assign(1, (uint16_t)hs->node_image[v]);
   if (in->n_images > 65535) {
     delete hs;
     return LFR_EUNSUPPORTED;
+  }
+  const bool small_sets = in->n_images <= 64;  // image set of a union-find root as one 64-bit mask
+  std::vector<uint64_t> mask(small_sets ? N : 0);
+  std::vector<std::vector<uint16_t>> imgs(small_sets ? 0 : N);
+  for (uint32_t v = 0; v < N; ++v) {
+    if (small_sets) mask[v] = 1ull << hs->node_image[v];
+    else imgs[v].assign(1, (uint16_t)hs->node_image[v]);
   }
   auto find = [&](uint32_t x) {
     uint32_t r = x;
@@ -302,9 +293,23 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     return r;
   };
   std::vector<uint16_t> merged;
-  for (uint64_t k : order) {
+  for (uint64_t oi = M; oi-- > 0;) {
+    const uint32_t k = order[oi];
     const uint32_t r1 = find(n1[k]), r2 = find(n2[k]);
     if (r1 == r2) continue;
+    if (small_sets) {
+      if (mask[r1] & mask[r2]) continue;  // set_intersection non-empty (solve.cc:507-511)
+      if (__builtin_popcountll(mask[r1]) < __builtin_popcountll(mask[r2])) {  // solve.cc:513-521
+        parent[r1] = (int32_t)r2;
+        mask[r2] |= mask[r1];
+        mask[r1] = 0;
+      } else {
+        parent[r2] = (int32_t)r1;
+        mask[r1] |= mask[r2];
+        mask[r2] = 0;
+      }
+      continue;
+    }
     const std::vector<uint16_t>&a = imgs[r1], &b = imgs[r2];
     bool clash = false;  // std::set_intersection non-empty (solve.cc:507-511)
     for (size_t i = 0, j = 0; i < a.size() && j < b.size();) {
@@ -360,7 +365,10 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   std::vector<uint32_t> ma, mb;
   std::vector<double> wsum;
   {
-    std::unordered_map<uint64_t, uint32_t> slot;
+    uint64_t n_inter = 0;
+    for (uint32_t v = 0; v < N; ++v)
+      for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e) n_inter += hs->track[v] != hs->track[hs->edges[e].dst];
+    FlatMap slot((size_t)n_inter);
     std::vector<uint64_t> keys;
     std::vector<double> sums;
     for (uint32_t v = 0; v < N; ++v) {
@@ -369,13 +377,14 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
         const uint32_t tt = hs->track[hs->edges[e].dst];
         if (ts == tt) continue;
         const uint64_t key = (uint64_t)ts * T + tt;
-        auto it = slot.find(key);
-        if (it == slot.end()) {
-          slot.emplace(key, (uint32_t)keys.size());
+        bool fresh;
+        const size_t sl = slot.find_or_insert(key, &fresh);
+        if (fresh) {
+          slot.vals[sl] = (uint32_t)keys.size();
           keys.push_back(key);
           sums.push_back((double)hs->edges[e].sim);
         } else {
-          sums[it->second] += (double)hs->edges[e].sim;  // accumulation in node / out-edge order
+          sums[slot.vals[sl]] += (double)hs->edges[e].sim;  // accumulation in node / out-edge order
         }
       }
     }
@@ -399,7 +408,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   std::vector<uint32_t> gc(cc);
   uint32_t next_label = n_cc;
   const uint32_t max_nodes = S.n_images_seen;
-  std::vector<std::vector<MetaEdge>> per_cc;
+  std::vector<std::vector<lfr::CutEdge>> per_cc;
   std::vector<int32_t> big_slot(n_cc, -1);
   for (uint32_t c = 0; c < n_cc; ++c)
     if (cc_nodes[c] > max_nodes) {
@@ -412,11 +421,12 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
       if (!(ma[i] < mb[i])) continue;  // undirected list, weight int(100 * sum sim) (solve.cc:327-330)
       const int32_t s = big_slot[cc[ma[i]]];
       if (s < 0) continue;
-      per_cc[s].push_back(MetaEdge{ma[i], mb[i], (int64_t)(100.0 * wsum[i])});
+      per_cc[s].push_back(lfr::CutEdge{ma[i], mb[i], (int64_t)(int)(100.0 * wsum[i])});  // static_cast<int>(100 * it.second), solve.cc:329
     }
+    lfr::CutWorkspace W;
     for (auto& edges : per_cc) {
       std::vector<std::vector<uint32_t>> groups;
-      recursive_cut(edges, nodes_in_track, max_nodes, &groups);
+      recursive_cut(std::move(edges), nodes_in_track, max_nodes, W, &groups);
       for (const auto& g : groups) {
         for (uint32_t t : g) gc[t] = next_label;
         ++next_label;

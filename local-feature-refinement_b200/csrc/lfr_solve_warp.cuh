@@ -44,7 +44,8 @@ struct DevProblem {
   double* st_cost1;
   uint32_t* st_ls;
   uint32_t* st_kept;  // kept directed edges E_c
-  unsigned long long* st_cycles;  // optional [8 per slot]: total, setup, eval, assemble, lm_step, line search (LFR_PROFILE=1)
+  unsigned long long* st_cycles;  // optional [8 per slot]: total, setup, eval, assemble, lm_step, line search (LFR_DBG_PROFILE)
+  unsigned long long* st_times;   // optional [2 per slot]: %globaltimer (ns) when the component's warp started / finished
 };
 
 struct WarpBucket {

@@ -18,8 +18,9 @@ The one piece that cannot follow the reference is the 2-way normalized cut:
 the reference calls colmap::ComputeNormalizedMinGraphCut (Graclus inside
 COLMAP, solve.cc:192), which is not in the reference repository nor in this
 image.  `two_way_cut` below is a deterministic replacement (BFS region growing
-balanced on track sizes); it only matters for meta-components larger than
-#images nodes, and the GPU path and the oracle share it.
+balanced on volume; like the COLMAP call it sees only the edge list and the integer weights,
+csrc/lfr_cut.h is the same definition); it only matters for meta-components larger than
+#images nodes, and the GPU path and every checker share it.
 """
 from __future__ import annotations
 
@@ -210,11 +211,14 @@ def _connected_components(n: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
     return rank[lab].astype(np.int64)
 
 
-def two_way_cut(nodes: List[int], adj: Dict[int, Dict[int, int]], node_weight) -> Dict[int, int]:
+def two_way_cut(nodes: List[int], adj: Dict[int, Dict[int, int]]) -> Dict[int, int]:
     """Deterministic stand-in for colmap::ComputeNormalizedMinGraphCut(edges,
-    weights, 2) (solve.cc:192).  `nodes` all have >= 1 edge inside `adj`.
+    weights, 2) (solve.cc:192) — like the COLMAP call a function of the edge list and the integer
+    edge weights only; balance is on volume (weighted degree).  Same definition as
+    csrc/lfr_cut.h (the two are tested to agree).  `nodes` all have >= 1 edge inside `adj`.
     Returns node -> {0, 1} with both sides non-empty (when len(nodes) >= 2)."""
     nodes = sorted(nodes)
+    vol = {x: sum(adj[x].values()) for x in nodes}
     # connected pieces of this sub-graph
     seen = set()
     pieces = []
@@ -234,17 +238,17 @@ def two_way_cut(nodes: List[int], adj: Dict[int, Dict[int, int]], node_weight) -
         pieces.append(comp)
     if len(pieces) > 1:
         # free cut: balance the pieces over the two sides, heaviest first
-        pieces.sort(key=lambda c: (-sum(node_weight[x] for x in c), c[0]))
+        pieces.sort(key=lambda c: (-sum(vol[x] for x in c), c[0]))
         w = [0, 0]
         out = {}
         for c in pieces:
             side = 0 if w[0] <= w[1] else 1
-            w[side] += sum(node_weight[x] for x in c)
+            w[side] += sum(vol[x] for x in c)
             for x in c:
                 out[x] = side
         return out
     # one connected piece: grow side 0 breadth-first from a pseudo-peripheral
-    # node, preferring strongly attached nodes, until it holds half the weight.
+    # node until it holds half the volume.
     def bfs_last(start):
         order = [start]
         mark = {start}
@@ -259,14 +263,14 @@ def two_way_cut(nodes: List[int], adj: Dict[int, Dict[int, int]], node_weight) -
         return order
     start = bfs_last(nodes[0])[-1]
     order = bfs_last(start)
-    total = sum(node_weight[x] for x in nodes)
+    total = sum(vol[x] for x in nodes)
     out = {}
     acc = 0
     for i, x in enumerate(order):
         if i > 0 and (acc * 2 >= total or i == len(order) - 1):
             break
         out[x] = 0
-        acc += node_weight[x]
+        acc += vol[x]
     for x in order:
         out.setdefault(x, 1)
     # one refinement sweep: move a node across if that lowers the cut and keeps both sides non-empty
@@ -297,7 +301,7 @@ def recursive_cut(edge_a, edge_b, edge_w, node_weight, max_weight) -> List[List[
             adj.setdefault(a, {})[b] = adj.setdefault(a, {}).get(b, 0) + w
             adj.setdefault(b, {})[a] = adj.setdefault(b, {}).get(a, 0) + w
         nodes = list(adj.keys())
-        side = two_way_cut(nodes, adj, node_weight)
+        side = two_way_cut(nodes, adj)
         for s in (0, 1):
             members = sorted(x for x in nodes if side[x] == s)
             if not members:
@@ -388,7 +392,7 @@ class Problem:
 def build_problem_native(ms: MatchSet, banned_images=(), log=None) -> Problem:
     """solve.cc:405-606 through the native host stage (csrc/lfr_host.cc, include/lfr_host.h)."""
     import ctypes as C
-    from .capi import load_b200
+    from .capi import load_host
 
     class HostInput(C.Structure):
         _fields_ = [("n_pairs", C.c_uint64), ("n_matches", C.c_uint64), ("n_images", C.c_uint32),
@@ -403,7 +407,7 @@ def build_problem_native(ms: MatchSet, banned_images=(), log=None) -> Problem:
                     ("n_cut_groups", C.c_uint32), ("reserved", C.c_uint32), ("n_edges", C.c_uint64),
                     ("tracks_ms", C.c_double), ("graph_cut_ms", C.c_double)]
 
-    L = load_b200().lib
+    L = load_host()
     L.lfr_host_stage_create.argtypes = [C.POINTER(HostInput), C.POINTER(C.c_void_p), C.POINTER(HostSizes)]
     L.lfr_host_stage_create.restype = C.c_int
     L.lfr_host_stage_export.argtypes = [C.c_void_p] * 11

@@ -1,6 +1,6 @@
 """types.proto I/O: MatchingFile in, SolutionFile out (solve.cc:412-481, 643-679).
 
-The bytes are decoded / encoded by the native codec in csrc/lfr_wire.cc through
+The bytes are decoded / encoded by the native codec in csrc/lfr_wire.cc (csrc/liblfr_host.so) through
 the C ABI of include/lfr_wire.h (no libprotobuf, no per-match Python loop).  A
 matches file may be split into `<path>.part.0, .part.1, ...`
 (compute_match_graph.py:189-205); like solve.cc:416-424 the parts are read only
@@ -14,7 +14,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from .capi import load_b200
+from .capi import load_host
 from .matchset import MatchSet
 
 
@@ -34,7 +34,7 @@ _bound = False
 
 def _lib():
     global _bound
-    L = load_b200().lib
+    L = load_host()
     if not _bound:
         L.lfr_wire_scan_matches.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.lfr_wire_scan_matches.restype = C.c_int

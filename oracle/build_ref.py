@@ -67,9 +67,31 @@ def build_cost(force: bool = False) -> str:
     return out
 
 
+def build_solve(force: bool = False, optimized: bool = False) -> str:
+    """solve.cc (+ cost.cc, which it #includes) + graph.cc -> oracle/_ref/solve: the reference's own
+    executable, with the shims' implementations linked in.  optimized=False follows the reference's
+    CMakeLists.txt:4 (no -O flag); optimized=True builds oracle/_ref/solve_O2 (-O2), the fairer CPU
+    baseline for bench.py's reference arm."""
+    out = os.path.join(OUT, "solve_O2" if optimized else "solve")
+    if not reference_available():
+        if os.path.exists(out):
+            return out
+        raise RuntimeError("%s is missing and %s is not present" % (out, REF_SRC))
+    srcs = [os.path.join(REF_SRC, "solve.cc"), os.path.join(REF_SRC, "graph.cc"),
+            os.path.join(SHIMS, "mini_ceres.cc"), os.path.join(SHIMS, "types_pb_shim.cc")]
+    deps = srcs + [os.path.join(REF_SRC, "cost.cc"), os.path.join(REF_SRC, "graph.h"),
+                   os.path.join(HERE, "..", "local-feature-refinement_b200", "csrc", "lfr_cut.h")] + _shim_files()
+    if not force and _newer(out, deps):
+        return out
+    os.makedirs(OUT, exist_ok=True)
+    cmd = [CXX, "-std=c++11", "-g", "-O2" if optimized else "-O0", "-ffp-contract=off", "-pthread",
+           "-I", SHIMS, "-I", REF_SRC, "-o", out] + srcs
+    subprocess.check_call(cmd)
+    return out
+
+
 def build(force: bool = False):
-    outs = [build_cost(force)]
-    return outs
+    return [build_cost(force), build_solve(force), build_solve(force, optimized=True)]
 
 
 if __name__ == "__main__":

@@ -1,15 +1,18 @@
 """Generate the golden fixtures under tests/golden/.
 
-The reference ships no golden vectors and cannot be built or imported here
-(C++ against Ceres/COLMAP), so these fixtures are produced by the
-CPU oracle (oracle/lfr_oracle.cc) — they pin the oracle and the CUDA path
-against silent drift, they do not pin either against a real Ceres binary.
+The reference ships no golden vectors.  `*_solution.pb` is therefore produced by running the
+REFERENCE'S OWN main() here: oracle/_ref/solve = multi-view-refinement/solve.cc + cost.cc + graph.cc
+compiled unmodified against the shim headers of oracle/ref_shims/ (oracle/build_ref.py; Ceres'
+minimizer restated in mini_ceres.cc, the Graclus cut replaced by csrc/lfr_cut.h — see DESIGN.md for
+what that does and does not pin).  `*_expected.npz` holds the restated oracle's per-component
+outputs (oracle/lfr_oracle.cc, literal line-search mode) for the same input; the script asserts
+that the oracle pipeline reproduces the reference binary's SolutionFile byte for byte.
 
     python tests/golden/make_golden.py
 
-writes, for each case, the MatchingFile bytes (`*_matches.pb`) and the
-oracle's outputs (`*_expected.npz`: positions, per-component iterations,
-termination codes, costs; SolutionFile bytes `*_solution.pb`).
+writes, for each case, the MatchingFile bytes (`*_matches.pb`), the reference binary's SolutionFile
+(`*_solution.pb`) and stdout (`*_stdout.txt`, timing lines removed), and the oracle's outputs
+(`*_expected.npz`: positions, per-component iterations, termination codes, costs).
 """
 import os
 import sys
@@ -36,17 +39,36 @@ def cases():
     yield "fountain_2pct", synth.generate("cfg2", scale=0.02, seed=7)
 
 
+def run_reference_binary(matches_path, out_path):
+    """oracle/_ref/solve on one input; returns its stdout without the timing lines."""
+    import importlib.util
+    import subprocess
+    spec = importlib.util.spec_from_file_location("lfr_build_ref", os.path.join(ROOT, "oracle", "build_ref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    exe = mod.build_solve()
+    r = subprocess.run([exe, "--matches_file", matches_path, "--output_file", out_path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return "".join(l + "\n" for l in r.stdout.splitlines() if " time:" not in l)
+
+
 def main():
     orc = load_oracle()
     for name, ms in cases():
         data = wire.encode_matching_file(ms)
-        with open(os.path.join(HERE, "%s_matches.pb" % name), "wb") as fh:
+        mpath = os.path.join(HERE, "%s_matches.pb" % name)
+        with open(mpath, "wb") as fh:
             fh.write(data)
+        spath = os.path.join(HERE, "%s_solution.pb" % name)
+        stdout = run_reference_binary(mpath, spath)          # the reference's own main()
+        with open(os.path.join(HERE, "%s_stdout.txt" % name), "w") as fh:
+            fh.write(stdout)
         p = build_problem(wire.decode_matching_file(data))
         pos, st = orc.solve(p, orc.default_options(n_threads=1))
         sol = assemble_solution(p, pos)
-        with open(os.path.join(HERE, "%s_solution.pb" % name), "wb") as fh:
-            fh.write(wire.encode_solution(sol.image_names, sol.fact, sol.img_ptr, sol.feature_idx, sol.di, sol.dj))
+        mine = wire.encode_solution(sol.image_names, sol.fact, sol.img_ptr, sol.feature_idx, sol.di, sol.dj)
+        with open(spath, "rb") as fh:
+            assert fh.read() == mine, "%s: the oracle pipeline and the reference binary disagree" % name
         np.savez_compressed(os.path.join(HERE, "%s_expected.npz" % name), positions=pos,
                             iterations=st["iterations"], termination=st["termination"],
                             initial_cost=st["initial_cost"], final_cost=st["final_cost"],

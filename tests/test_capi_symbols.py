@@ -17,15 +17,31 @@ def declared(header):
 
 
 def test_every_declared_symbol_is_exported(b200):
-    names = sorted(set(declared("lfr.h") + declared("lfr_wire.h") + declared("lfr_host.h")))
-    assert "lfr_solve" in names and "lfr_wire_decode_matches" in names and "lfr_host_stage_create" in names
-    for n in names:
+    """include/lfr.h -> csrc/liblfr_b200.so (the product); include/lfr_wire.h and include/lfr_host.h ->
+    csrc/liblfr_host.so (CPU-only host utilities)."""
+    from lfr_b200.capi import ABI_SYMBOLS, load_host
+    from lfr_b200.wire import WIRE_SYMBOLS
+    core = declared("lfr.h")
+    assert "lfr_solve" in core
+    for n in core:
         assert hasattr(b200.lib, n), n
     assert b200.backend == "b200"
-    from lfr_b200.capi import ABI_SYMBOLS
-    from lfr_b200.wire import WIRE_SYMBOLS
+    assert sorted(ABI_SYMBOLS) == core
+    host_lib = load_host()
+    host_names = sorted(set(declared("lfr_wire.h") + declared("lfr_host.h")))
+    assert "lfr_wire_decode_matches" in host_names and "lfr_host_stage_create" in host_names
+    for n in host_names:
+        assert hasattr(host_lib, n), n
     host = ["lfr_host_stage_create", "lfr_host_stage_export", "lfr_host_stage_destroy"]
-    assert sorted(ABI_SYMBOLS + WIRE_SYMBOLS + host) == names
+    assert sorted(WIRE_SYMBOLS + host) == host_names
+
+
+def test_host_library_has_no_cuda_dependency():
+    import subprocess
+    from lfr_b200.capi import HOST_LIB_PATH, load_host
+    load_host()
+    out = subprocess.check_output(["ldd", HOST_LIB_PATH]).decode()
+    assert "cuda" not in out.lower() and "nvidia" not in out.lower(), out
 
 
 def test_oracle_exports_the_same_abi(oracle):
