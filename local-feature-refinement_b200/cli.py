@@ -29,32 +29,91 @@ USAGE = """Options:
 """
 
 
-class _Parser(argparse.ArgumentParser):
-    def error(self, message):  # solve.cc:397-401
-        sys.stderr.write("ERROR: %s\n\n" % message)
-        sys.stderr.write(USAGE)
-        raise SystemExit(1)
+class _CliError(Exception):
+    pass
+
+
+# (name, takes an argument, repeatable) — solve.cc:379-385 plus the opt-in extras
+_OPTIONS = [("help", False, False), ("matches_file", True, False), ("output_file", True, False),
+            ("n_threads", True, False), ("banned_images", True, True),
+            ("device", True, False), ("gpus", True, False), ("stats_json", True, False)]
+
+
+def _find_option(name):
+    """Exact name, else unambiguous prefix (Boost.Program_options' default allow_guessing)."""
+    hits = [o for o in _OPTIONS if o[0].startswith(name)]
+    for o in _OPTIONS:
+        if o[0] == name:
+            return o
+    if len(hits) == 1:
+        return hits[0]
+    if len(hits) > 1:
+        raise _CliError("option '--%s' is ambiguous" % name)
+    raise _CliError("unrecognised option '--%s'" % name)
+
+
+def _parse(argv):
+    """Boost.Program_options semantics of solve.cc:387-401 (long options, `--name value` or
+    `--name=value`, no positional arguments), with Boost's error messages."""
+    vals = {}
+    i = 0
+    while i < len(argv):
+        tok = argv[i]
+        i += 1
+        if tok.startswith("--") and len(tok) > 2:
+            name, eq, adjacent = tok[2:].partition("=")
+            oname, takes, repeat = _find_option(name)
+            if takes:
+                if eq:
+                    v = adjacent
+                elif i < len(argv) and not (argv[i].startswith("-") and len(argv[i]) > 1):
+                    v = argv[i]
+                    i += 1
+                else:
+                    raise _CliError("the required argument for option '--%s' is missing" % oname)
+                if repeat:
+                    vals.setdefault(oname, []).append(v)
+                elif oname in vals:
+                    raise _CliError("option '--%s' cannot be specified more than once" % oname)
+                else:
+                    vals[oname] = v
+            else:
+                if eq:
+                    raise _CliError("option '--%s' does not take any arguments" % oname)
+                vals[oname] = True
+        elif tok.startswith("-") and len(tok) > 1:
+            raise _CliError("unrecognised option '%s'" % tok)
+        else:
+            raise _CliError("too many positional options have been specified on the command line")
+    return vals
+
+
+def _as_uint(vals, name, default):
+    if name not in vals:
+        return default
+    v = vals[name]
+    if not v.isdigit():      # lexical_cast<size_t>
+        raise _CliError("the argument ('%s') for option '--%s' is invalid" % (v, name))
+    return int(v)
 
 
 def parse_args(argv):
-    ap = _Parser(prog="solve", add_help=False)
-    ap.add_argument("--help", action="store_true")
-    ap.add_argument("--matches_file")
-    ap.add_argument("--output_file")
-    ap.add_argument("--n_threads", type=int, default=8)
-    ap.add_argument("--banned_images", action="append", default=[])
-    ap.add_argument("--device", type=int, default=0)
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--stats_json", default=None)
-    args = ap.parse_args(argv)
-    if args.help:
-        sys.stdout.write("Patch Match graph problem solver\n\n" + USAGE)
-        raise SystemExit(0)
-    if args.matches_file is None:
-        ap.error("the option '--matches_file' is required but missing")
-    if args.output_file is None:
-        ap.error("the option '--output_file' is required but missing")
-    return args
+    try:
+        vals = _parse(list(argv))
+        if vals.get("help"):
+            sys.stdout.write("Patch Match graph problem solver\n\n" + USAGE)
+            raise SystemExit(0)
+        for req in ("matches_file", "output_file"):        # po::notify: required options, in declaration order
+            if req not in vals:
+                raise _CliError("the option '--%s' is required but missing" % req)
+        return argparse.Namespace(
+            matches_file=vals["matches_file"], output_file=vals["output_file"],
+            n_threads=_as_uint(vals, "n_threads", 8), banned_images=vals.get("banned_images", []),
+            device=_as_uint(vals, "device", 0), gpus=_as_uint(vals, "gpus", 1), stats_json=vals.get("stats_json"))
+    except _CliError as e:                                  # solve.cc:397-401
+        sys.stderr.write("ERROR: %s\n\n" % e)
+        sys.stderr.write(USAGE)
+        raise SystemExit(1)
 
 
 def main(argv=None) -> int:

@@ -1311,10 +1311,10 @@ struct RecordDumper {
     if (!f) return;
     for (size_t i = 0; i < g_records.size(); ++i) {
       const shim::Record& r = g_records[i];
-      std::fprintf(f, "%llu %d %d %d %.17g %.17g %d %d\n", (unsigned long long)(size_t)r.first_parameter_block,
+      std::fprintf(f, "%llu %d %d %d %.17g %.17g %d %d %.17g\n", (unsigned long long)(size_t)r.first_parameter_block,
                    r.summary.num_iterations, (int)r.summary.termination_type, r.summary.num_line_search_steps,
                    r.summary.initial_cost, r.summary.final_cost, r.summary.num_parameter_blocks_reduced,
-                   r.summary.num_residual_blocks_reduced);
+                   r.summary.num_residual_blocks_reduced, r.summary.fixed_cost);
     }
     std::fclose(f);
   }
