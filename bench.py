@@ -17,10 +17,16 @@ N>1 (torchrun, one rank per GPU) every rank solves its own Fountain-scale scene
             the timed region
   roofline  algorithmic bytes (sum_c iters_c (80 E_c + 36 N_c)) / kernel time
             against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline  the CPU oracle (oracle/, a restatement of the reference's
-            Ceres solve — the reference itself cannot be built here) on the host cores
+  cpu_baseline  the CPU oracle (oracle/lfr_oracle.cc, the specialised restatement) on the host
+            cores: all cores, the reference's default 8 threads (solve.cc:384) and 1 thread
+  total_scope   host graph stage (tracks, roots, cut, dispatch: solve.cc:487-606) + solve = the
+            reference's "Total time" scope (solve.cc:487-641), for the B200 path and for the CPU
 
---impl reference times that CPU oracle as the reference arm.
+--impl reference times the reference's OWN solve: oracle/_ref/solve_O2 = multi-view-refinement/
+solve.cc + cost.cc + graph.cc compiled unmodified (-O2) against the shim headers of oracle/ref_shims/
+(Ceres' minimizer restated, see oracle/build_ref.py), on all host cores, "Solver time" scope
+(thread pool creation -> Wait(), solve.cc:615-638, measured in microseconds by the pool shim).
+Falls back to the oracle port when that binary was not built.
 """
 import argparse
 import json
@@ -71,15 +77,15 @@ def build_workload(name, seed=None):
     return p, refined_track_count(p)
 
 
-def workload_config(name, p, n_tracks, extra=None):
+def workload_config(name, p, n_tracks, n_gpus=1):
+    """The same keys and values from both arms (the driver compares the two configs)."""
     sizes = np.diff(p.comp_ptr.astype(np.int64))
-    cfg = {"workload": WORKLOADS.get(name, name), "nodes": int(p.graph.n_nodes),
-           "directed_edges": int(p.graph.n_edges), "tracks": int(p.info.get("n_tracks", 0)),
-           "tracks_refined": int(n_tracks), "components_solved": int((sizes > 1).sum()),
-           "max_component_nodes": int(sizes.max()) if sizes.size else 0}
-    if extra:
-        cfg.update(extra)
-    return cfg
+    return {"workload": WORKLOADS.get(name, name), "nodes": int(p.graph.n_nodes),
+            "directed_edges": int(p.graph.n_edges), "tracks": int(p.info.get("n_tracks", 0)),
+            "tracks_refined": int(n_tracks), "components_solved": int((sizes > 1).sum()),
+            "max_component_nodes": int(sizes.max()) if sizes.size else 0,
+            "per_gpu": "one scene per GPU" if n_gpus > 1 else "single scene",
+            "l2": "flushed between timed steps (256 MiB write, untimed)"}
 
 
 class ClockSampler:
@@ -216,56 +222,110 @@ def pinned_problem(lib, p):
     return s2, pinned, pos, h2d
 
 
+def reference_binary():
+    """oracle/_ref/solve_O2 (built by oracle/build_ref.py where /root/reference exists; shipped to the
+    GPU box as a file), or None."""
+    path = os.path.join(ROOT, "oracle", "_ref", "solve_O2")
+    return path if os.path.exists(path) and os.access(path, os.X_OK) else None
+
+
+def time_reference_binary(exe, matches_path, n_threads, repeats, tmpdir):
+    """Runs the reference's main() `repeats` times; returns (solver_ms list, total_ms list, graph_cut_ms
+    list, iterations-independent): "Solver time" scope from the pool shim's microsecond timer,
+    "Total time" / "Graph-cut time" from the program's own stdout (whole milliseconds)."""
+    solver, total, cut = [], [], []
+    timing = os.path.join(tmpdir, "pool_timing.txt")
+    for _ in range(repeats):
+        if os.path.exists(timing):
+            os.unlink(timing)
+        env = dict(os.environ, LFR_POOL_TIMING_FILE=timing)
+        r = subprocess.run([exe, "--matches_file", matches_path, "--output_file", os.path.join(tmpdir, "ref_solution.pb"),
+                            "--n_threads", str(n_threads)], capture_output=True, text=True, env=env)
+        if r.returncode != 0:
+            raise RuntimeError("reference binary failed: %s" % r.stderr[-300:])
+        with open(timing) as fh:
+            solver.append(float(fh.read().split()[0]))
+        for line in r.stdout.splitlines():
+            if line.startswith("Total time:"):
+                total.append(float(line.split()[2].rstrip("ms")))
+            if line.startswith("Graph-cut time:"):
+                cut.append(float(line.split()[2].rstrip("ms")))
+    return solver, total, cut
+
+
 def run_reference(args):
-    """Reference arm: the reference's CPU solve (solve.cc:614-635 on a thread
-    pool), i.e. the restated oracle — the Ceres/COLMAP build is unavailable here."""
+    """Reference arm: the reference's own CPU solve on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_util import load_oracle
-    orc = load_oracle()
     cores = os.cpu_count() or 1
     # the B200 arm at --gpus N solves N scenes (one per GPU, weak scaling): same work here
-    from lfr_b200 import synth
+    from lfr_b200 import build_problem, refined_track_count, synth, wire
     base_seed = synth.CONFIGS[synth.ALIASES.get(args.workload, args.workload)].seed
-    scenes = [build_workload(args.workload, seed=(base_seed + 7919 * r) if args.gpus > 1 else None)
-              for r in range(max(1, args.gpus))]
-    p, n_tracks = scenes[0]
-    n_tracks = sum(t for _, t in scenes)
-    o = orc.default_options(n_threads=cores)
-    t_w = time.perf_counter()
-    n_w = 0
-    while n_w < max(args.warmup, 3) or time.perf_counter() - t_w < 1.5:   # host threads / clocks settle
-        for q, _ in scenes:
-            orc.solve(q, o)
-        n_w += 1
-    t = []
-    iters = 0
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        iters = 0
-        for q, _ in scenes:
-            _, st = orc.solve(q, o)
-            iters += st["total_iterations"]
-        t.append(time.perf_counter() - t0)
+    tmpdir = tempfile.mkdtemp(prefix="lfr_ref_")
+    scenes = []
+    for r in range(max(1, args.gpus)):
+        ms = synth.generate(args.workload, seed=(base_seed + 7919 * r) if args.gpus > 1 else None)
+        p = build_problem(ms)                       # host utilities only (csrc/liblfr_host.so): no CUDA library is mapped
+        path = os.path.join(tmpdir, "matches_%d.pb" % r)
+        with open(path, "wb") as fh:
+            fh.write(wire.encode_matching_file(ms))
+        scenes.append((p, refined_track_count(p), path))
+    p0 = scenes[0][0]
+    n_tracks = sum(t for _, t, _ in scenes)
+    exe = reference_binary()
+    warm = max(args.warmup, 3)
+    extra = {}
+    if exe is not None:
+        kind = "reference"
+        for _, _, path in scenes:
+            time_reference_binary(exe, path, cores, warm, tmpdir)
+        per_scene = [time_reference_binary(exe, path, cores, args.steps, tmpdir) for _, _, path in scenes]
+        t = [sum(ps[0][k] for ps in per_scene) / 1e3 for k in range(args.steps)]          # seconds per step
+        tot = [sum(ps[1][k] for ps in per_scene) for k in range(args.steps)]
+        eight = time_reference_binary(exe, scenes[0][2], 8, min(args.steps, 5), tmpdir)
+        one = time_reference_binary(exe, scenes[0][2], 1, 1, tmpdir)
+        extra = {"total_scope_ms_per_step": float(np.median(tot)),
+                 "graph_cut_ms": float(np.median(per_scene[0][2])) if per_scene[0][2] else None,
+                 "eight_thread_ms_per_scene": float(np.median(eight[0])), "single_thread_ms_per_scene": float(one[0][0])}
+        sample = ("whole workload x %d steps: oracle/_ref/solve_O2 = the reference's solve.cc + cost.cc + graph.cc "
+                  "compiled unmodified (-O2; the reference's own build sets no -O flag) against shim headers, "
+                  "Ceres' minimizer restated (oracle/ref_shims/mini_ceres.cc); 'Solver time' scope" % args.steps)
+        from_oracle = None
+    else:
+        kind = "port"
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_util import load_oracle
+        orc = load_oracle()
+        o = orc.default_options(n_threads=cores)
+        for _ in range(warm):
+            for q, _, _ in scenes:
+                orc.solve(q, o)
+        t = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            for q, _, _ in scenes:
+                orc.solve(q, o)
+            t.append(time.perf_counter() - t0)
+        sample = ("whole workload x %d steps: Ceres-1.14-semantics CPU oracle (oracle/lfr_oracle.cc, -O2); "
+                  "oracle/_ref/solve_O2 was not built" % args.steps)
     # median of the K steps: the host-side pool is sensitive to other tenants of the box; the median
     # is the conservative (faster) reading of the reference
     ms = 1e3 * float(np.median(t))
     value = n_tracks / (ms / 1e3)
+    cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+    cpu.update(extra)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "ms_per_step_mean": 1e3 * float(np.mean(t)),
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms, "ms_per_step_mean": 1e3 * float(np.mean(t)),
             "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.workload, p, n_tracks),
-            "lm_iters_per_s": iters / (ms / 1e3),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "whole workload, %d steps; Ceres-1.14-semantics CPU oracle "
-                                       "(oracle/lfr_oracle.cc, -O2) — the reference's Ceres/COLMAP "
-                                       "build is unavailable in this image" % args.steps},
+            "config": workload_config(args.workload, p0, scenes[0][1], args.gpus),
+            "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+    import shutil
+    shutil.rmtree(tmpdir, ignore_errors=True)
     return 0
 
 
@@ -383,14 +443,28 @@ def run_b200(args):
     t1 = time.perf_counter()
     orc.solve(p, orc.default_options(n_threads=1))   # per-core figure
     cpu_1t_ms = 1e3 * (time.perf_counter() - t1)
+    o8 = orc.default_options(n_threads=8)            # the reference's default --n_threads (solve.cc:384)
+    c8 = []
+    for _ in range(7):
+        t1 = time.perf_counter()
+        orc.solve(p, o8)
+        c8.append(time.perf_counter() - t1)
+    cpu_8t_ms = 1e3 * float(np.median(c8))
+    # "Total time" scope (solve.cc:487-641): tracks + roots + graph cut + dispatch + solve.  Host stage =
+    # csrc/lfr_host.cc (single-threaded C++), timed by its own phase clocks over 5 runs.
+    from lfr_b200 import build_problem, synth
+    ms_scene = synth.generate(args.workload, seed=base_seed + 7919 * rank if world > 1 else None)
+    hs = []
+    for _ in range(5):
+        q = build_problem(ms_scene)
+        hs.append(q.info["tracks_ms"] + q.info["graph_cut_ms"] + q.info["dispatch_ms"])
+    host_stage_ms = float(np.median(hs))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.workload, p, n_tracks, {
-            "per_gpu": "one scene per GPU" if world > 1 else "single scene",
-            "l2": "flushed between timed steps (256 MiB write, untimed)",
-            "lm_iterations_per_step": int(st["total_iterations"])}),
+        "config": workload_config(args.workload, p, n_tracks, world),
+        "lm_iterations_per_step": int(st["total_iterations"]),
         "lm_iters_per_s": tot_iters / (ms_per_step / 1e3),
         "ms_per_step_median": ms_per_step_median,
         "e2e": {"value": tot_tracks / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -407,8 +481,13 @@ def run_b200(args):
         "cpu_baseline": {"value": n_tracks / (cpu_ms / 1e3), "unit": UNIT, "cores": cores, "kind": "port",
                          "ms_per_step": cpu_ms, "single_thread_value": n_tracks / (cpu_1t_ms / 1e3),
                          "single_thread_ms_per_step": cpu_1t_ms,
+                         "eight_thread_value": n_tracks / (cpu_8t_ms / 1e3), "eight_thread_ms_per_step": cpu_8t_ms,
                          "sample": "whole workload x %d repetitions (Ceres-1.14-semantics CPU oracle, "
-                                   "oracle/lfr_oracle.cc)" % reps},
+                                   "oracle/lfr_oracle.cc); the reference's own solve.cc is timed by --impl reference" % reps},
+        "total_scope": {"definition": "solve.cc:487-641 'Total time': tracks + roots + graph cut + dispatch + solve",
+                        "host_stage_ms": host_stage_ms, "b200_ms": host_stage_ms + e2e_ms,
+                        "cpu_oracle_ms_all_cores": host_stage_ms + cpu_ms, "cpu_oracle_ms_8_threads": host_stage_ms + cpu_8t_ms,
+                        "host_stage": "csrc/lfr_host.cc, single-threaded C++ (same stage feeds both)"},
         "clocks": clocks,
     }
     print(json.dumps(line))

@@ -45,7 +45,8 @@ typedef struct lfr_host_sizes {
   uint32_t n_nodes, n_tracks, n_components, n_images_seen, max_track_size, max_component_size;
   uint32_t n_meta_components, n_oversized_meta_components, n_cut_groups, reserved;
   uint64_t n_edges;
-  double tracks_ms, graph_cut_ms;
+  double tracks_ms, graph_cut_ms;   /* solve.cc:487-582 (sort, Kruskal, roots) and :585-589 ("Graph-cut time") */
+  double graph_ms, dispatch_ms;     /* node interning + edge lists (:438-481); dispatch list (:594-604)     */
 } lfr_host_sizes;
 
 /* Run the whole stage.  Returns 0 or LFR_E*. */

@@ -187,6 +187,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   lfr_host_stage* hs = new lfr_host_stage();
   lfr_host_sizes S;
   std::memset(&S, 0, sizeof S);
+  const auto t_graph = Clock::now();
   // ---- H1: node interning + directed edges (solve.cc:438-481) -----------------------------
   std::vector<uint64_t> kept_matches;  // indices of matches of non-skipped pairs, in order
   std::vector<uint32_t> m_img1, m_img2;
@@ -261,6 +262,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     if (sz) *sz = S;
     return LFR_OK;
   }
+  S.graph_ms = ms_since(t_graph);
   const auto t_tracks = Clock::now();
   // ---- H2: constrained Kruskal (solve.cc:489-541) ------------------------------------------
   // std::sort + std::reverse on (sim, n1, n2) (solve.cc:489-490): ascending radix sort, walked backwards
@@ -442,6 +444,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   for (uint32_t v = 0; v < N; ++v) hs->comp[v] = final_cc[hs->track[v]];
   hs->C = n_final;
   S.graph_cut_ms = ms_since(t_cut);
+  const auto t_disp = Clock::now();
   // ---- H5: dispatch list (solve.cc:594-604) ----------------------------------------------------
   std::vector<uint32_t> sizes(n_final, 0);
   for (uint32_t v = 0; v < N; ++v) ++sizes[hs->comp[v]];
@@ -460,6 +463,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     std::vector<uint32_t> fill(hs->comp_ptr.begin(), hs->comp_ptr.end() - 1);
     for (uint32_t v = 0; v < N; ++v) hs->comp_nodes[fill[slot_of[hs->comp[v]]]++] = v;  // ascending node index
   }
+  S.dispatch_ms = ms_since(t_disp);
   S.n_nodes = N;
   S.n_edges = hs->E;
   S.n_tracks = T;

@@ -144,19 +144,10 @@ struct CandNorms {
 // search, accumulated per edge from the same evaluation:
 //   grad . dl = sum_e a_e r_e^T (dl_dst - M_e dl_src)      (J_src = -M, J_dst = I)
 // so a line-search trial needs no separate gradient assembly pass.
-// ONE out-of-line body for every evaluation of the solve (iteration 0, candidates, line-search
-// trials): the kernel's instruction footprint is what limits a warp that runs alone on its
-// scheduler (instruction-fetch stalls), so the modes are runtime flags, not template copies.
-constexpr int kEvalDirDeriv = 1, kEvalNorms = 2;
-__device__ __noinline__ double eval_pass2(const Warp2Ctx& C, const double* xe, const DevConsts& K, int flags,
-                                          double* dphi, CandNorms* nrm) {
-  double v[4] = {0.0, 0.0, 0.0, 0.0};  // cost, grad . dl, |x - xc|^2, |xc|^2
-  if (flags & kEvalNorms) {
-    v[2] = nrm->dn2;
-    v[3] = nrm->xn2;
-  }
-  const bool dirderiv = (flags & kEvalDirDeriv) != 0;
-#pragma unroll 1
+template <bool DIRDERIV, bool NORMS>
+__device__ __forceinline__ double eval_pass2(const Warp2Ctx& C, const double* xe, const DevConsts& K,
+                                             double* dphi = nullptr, CandNorms* nrm = nullptr) {
+  double cost = 0.0, dd = 0.0;
   for (int j = C.lane; j < C.Ec; j += 32) {
     const uint32_t mt = C.meta[j];
     const int s = mt & 0xfff, d = (mt >> 12) & 0xfff, kind = mt >> 24;
@@ -173,157 +164,161 @@ __device__ __noinline__ double eval_pass2(const Warp2Ctx& C, const double* xe, c
     sc[4 * C.emax] = ev.m01;
     sc[5 * C.emax] = ev.m10;
     sc[6 * C.emax] = ev.m11;
-    v[0] += ev.half_rho;
-    if (dirderiv) {
+    cost += ev.half_rho;
+    if (DIRDERIV) {
       const int fs = C.freeof[s], fd = C.freeof[d];
       const double s0 = fs >= 0 ? C.dl[2 * fs] : 0.0, s1 = fs >= 0 ? C.dl[2 * fs + 1] : 0.0;
       const double d0 = fd >= 0 ? C.dl[2 * fd] : 0.0, d1 = fd >= 0 ? C.dl[2 * fd + 1] : 0.0;
-      v[1] += ev.a * (ev.r0 * (d0 - (ev.m00 * s0 + ev.m01 * s1)) + ev.r1 * (d1 - (ev.m10 * s0 + ev.m11 * s1)));
+      dd += ev.a * (ev.r0 * (d0 - (ev.m00 * s0 + ev.m01 * s1)) + ev.r1 * (d1 - (ev.m10 * s0 + ev.m11 * s1)));
     }
   }
-  warp_sum_n<4>(v);
-  if (dirderiv) *dphi = v[1];
-  if (flags & kEvalNorms) {
+  if (DIRDERIV && NORMS) {
+    double v[4] = {cost, dd, nrm->dn2, nrm->xn2};
+    warp_sum_n<4>(v);
+    cost = v[0];
+    *dphi = v[1];
     nrm->dn2 = v[2];
     nrm->xn2 = v[3];
+  } else if (NORMS) {
+    double v[3] = {cost, nrm->dn2, nrm->xn2};
+    warp_sum_n<3>(v);
+    cost = v[0];
+    nrm->dn2 = v[1];
+    nrm->xn2 = v[2];
+  } else if (DIRDERIV) {
+    warp_sum2(cost, dd);
+    *dphi = dd;
+  } else {
+    cost = warp_sum(cost);
   }
   __syncwarp();
-  return v[0];
+  return cost;
 }
 
-// Serial assembly for inputs whose edges do not come in clean (src->dst, dst->src) pairs
-// (duplicate pairs): one lane accumulates every edge in order.  Cold path, out of line.
-__device__ __noinline__ double assemble2_irregular(const Warp2Ctx& C, bool first, bool grad_only, const DevConsts& K) {
-  const int E = C.emax, ldh = C.ldh;
-  if (C.lane == 0) {
-    for (int i = 0; i < C.n; ++i) C.g[i] = 0.0;
-    for (int e = 0; e < C.Ec; ++e) {
-      const uint32_t mt = C.meta[e];
-      const int fs = C.freeof[mt & 0xfff], fd = C.freeof[(mt >> 12) & 0xfff];
-      const double a = C.scr[e], r0 = C.scr[E + e], r1 = C.scr[2 * E + e];
-      const double m00 = C.scr[3 * E + e], m01 = C.scr[4 * E + e], m10 = C.scr[5 * E + e],
-                   m11 = C.scr[6 * E + e];
-      if (fs >= 0) {
-        C.g[2 * fs] -= a * (m00 * r0 + m10 * r1);
-        C.g[2 * fs + 1] -= a * (m01 * r0 + m11 * r1);
-        if (!grad_only) {
-          double* hd = C.H + (2 * fs) * ldh + 2 * fs;
-          hd[0] += a * (m00 * m00 + m10 * m10);
-          hd[1] += a * (m00 * m01 + m10 * m11);
-          hd[ldh] += a * (m00 * m01 + m10 * m11);
-          hd[ldh + 1] += a * (m01 * m01 + m11 * m11);
-        }
-      }
-      if (fd >= 0) {
-        C.g[2 * fd] += a * r0;
-        C.g[2 * fd + 1] += a * r1;
-        if (!grad_only) {
-          C.H[(2 * fd) * ldh + 2 * fd] += a;
-          C.H[(2 * fd + 1) * ldh + 2 * fd + 1] += a;
-        }
-      }
-      if (!grad_only && fs >= 0 && fd >= 0) {
-        double* h0 = C.H + (2 * fs) * ldh + 2 * fd;
-        double* h1 = C.H + (2 * fd) * ldh + 2 * fs;
-        h0[0] -= a * m00; h0[1] -= a * m10; h0[ldh] -= a * m01; h0[ldh + 1] -= a * m11;
-        h1[0] -= a * m00; h1[1] -= a * m01; h1[ldh] -= a * m10; h1[ldh + 1] -= a * m11;
-      }
-    }
-  }
-  __syncwarp();
-  double acc = 0.0, gmax = 0.0;
-  for (int i = C.lane; i < C.n; i += 32) {
-    if (grad_only) {
-      acc += C.g[i] * C.dl[i];
-    } else {
-      if (first) C.S[i] = 1.0 / (1.0 + sqrt(C.H[i * ldh + i]));
-      const int l = C.lof[i >> 1];
-      const double xi = C.x[2 * l + (i & 1)];
-      const double p = fmin(fmax(xi - C.g[i], -K.bound), K.bound);
-      gmax = fmax(gmax, fabs(xi - p));
-    }
-  }
-  __syncwarp();
-  if (grad_only) return warp_sum(acc);
-  return warp_max(gmax);
-}
-
-// From the staged evaluation: grad_only = false -> H (unscaled, full symmetric),
+// From the staged evaluation: GRAD_ONLY = false -> H (unscaled, full symmetric),
 // g, on the first call the Jacobi scaling S; returns |x - P(x - g)|_inf.
-// grad_only = true -> returns grad . dl (phi'(alpha) of the line search).
-// One out-of-line body (see eval_pass2).
-__device__ __noinline__ double assemble2(const Warp2Ctx& C, bool first, bool grad_only, const DevConsts& K) {
+// GRAD_ONLY = true -> returns grad . dl (phi'(alpha) of the line search).
+template <bool GRAD_ONLY>
+__device__ __forceinline__ double assemble2(const Warp2Ctx& C, bool first, const DevConsts& K) {
   const int E = C.emax, ldh = C.ldh;
-  if (!grad_only) {
-#pragma unroll 1
+  if (!GRAD_ONLY) {
     for (int i = C.lane; i < C.n * ldh; i += 32) C.H[i] = 0.0;
     __syncwarp();
   }
-  if (C.irregular) return assemble2_irregular(C, first, grad_only, K);
-#pragma unroll 1
-  for (int e = C.lane; e < C.Ec; e += 32) {
-    const uint32_t mt = C.meta[e];
-    const int fs = C.freeof[mt & 0xfff], fd = C.freeof[(mt >> 12) & 0xfff];
-    const int t = C.twin[e];
-    const double a = C.scr[e], r0 = C.scr[E + e], r1 = C.scr[2 * E + e];
-    const double m00 = C.scr[3 * E + e], m01 = C.scr[4 * E + e], m10 = C.scr[5 * E + e],
-                 m11 = C.scr[6 * E + e];
-    const double at = C.scr[t], rt0 = C.scr[E + t], rt1 = C.scr[2 * E + t];
-    // contribution of e (as out-edge of its source) and of its twin (as in-edge of the same node)
-    C.tup[3 * E + e] = at * rt0 - a * (m00 * r0 + m10 * r1);
-    C.tup[4 * E + e] = at * rt1 - a * (m01 * r0 + m11 * r1);
-    if (!grad_only) {
-      C.tup[e] = a * (m00 * m00 + m10 * m10) + at;
-      C.tup[E + e] = a * (m00 * m01 + m10 * m11);
-      C.tup[2 * E + e] = a * (m01 * m01 + m11 * m11) + at;
-      if (fs >= 0 && fd >= 0) {  // block (fs, fd) = -a M^T - a_t M_t
-        const double t00 = C.scr[3 * E + t], t01 = C.scr[4 * E + t], t10 = C.scr[5 * E + t],
-                     t11 = C.scr[6 * E + t];
-        double* h0 = C.H + (2 * fs) * ldh + 2 * fd;
-        h0[0] = -a * m00 - at * t00;
-        h0[1] = -a * m10 - at * t01;
-        h0[ldh] = -a * m01 - at * t10;
-        h0[ldh + 1] = -a * m11 - at * t11;
+  if (!C.irregular) {
+    for (int e = C.lane; e < C.Ec; e += 32) {
+      const uint32_t mt = C.meta[e];
+      const int fs = C.freeof[mt & 0xfff], fd = C.freeof[(mt >> 12) & 0xfff];
+      const int t = C.twin[e];
+      const double a = C.scr[e], r0 = C.scr[E + e], r1 = C.scr[2 * E + e];
+      const double m00 = C.scr[3 * E + e], m01 = C.scr[4 * E + e], m10 = C.scr[5 * E + e],
+                   m11 = C.scr[6 * E + e];
+      const double at = C.scr[t], rt0 = C.scr[E + t], rt1 = C.scr[2 * E + t];
+      // contribution of e (as out-edge of its source) and of its twin (as in-edge of the same node)
+      C.tup[3 * E + e] = at * rt0 - a * (m00 * r0 + m10 * r1);
+      C.tup[4 * E + e] = at * rt1 - a * (m01 * r0 + m11 * r1);
+      if (!GRAD_ONLY) {
+        C.tup[e] = a * (m00 * m00 + m10 * m10) + at;
+        C.tup[E + e] = a * (m00 * m01 + m10 * m11);
+        C.tup[2 * E + e] = a * (m01 * m01 + m11 * m11) + at;
+        if (fs >= 0 && fd >= 0) {  // block (fs, fd) = -a M^T - a_t M_t
+          const double t00 = C.scr[3 * E + t], t01 = C.scr[4 * E + t], t10 = C.scr[5 * E + t],
+                       t11 = C.scr[6 * E + t];
+          double* h0 = C.H + (2 * fs) * ldh + 2 * fd;
+          h0[0] = -a * m00 - at * t00;
+          h0[1] = -a * m10 - at * t01;
+          h0[ldh] = -a * m01 - at * t10;
+          h0[ldh + 1] = -a * m11 - at * t11;
+        }
       }
     }
+    __syncwarp();
   }
-  __syncwarp();
   double acc = 0.0, gmax = 0.0;
-#pragma unroll 1
-  for (int f = C.lane; f < C.nf; f += 32) {
-    const int l = C.lof[f];
-    double d00 = 0., d01 = 0., d11 = 0., g0 = 0., g1 = 0.;
-#pragma unroll 1
-    for (int j = C.outptr[l]; j < C.outptr[l + 1]; ++j) {
-      g0 += C.tup[3 * E + j];
-      g1 += C.tup[4 * E + j];
-      if (!grad_only) {
-        d00 += C.tup[j];
-        d01 += C.tup[E + j];
-        d11 += C.tup[2 * E + j];
+  if (!C.irregular) {
+    for (int f = C.lane; f < C.nf; f += 32) {
+      const int l = C.lof[f];
+      double d00 = 0., d01 = 0., d11 = 0., g0 = 0., g1 = 0.;
+      for (int j = C.outptr[l]; j < C.outptr[l + 1]; ++j) {
+        g0 += C.tup[3 * E + j];
+        g1 += C.tup[4 * E + j];
+        if (!GRAD_ONLY) {
+          d00 += C.tup[j];
+          d01 += C.tup[E + j];
+          d11 += C.tup[2 * E + j];
+        }
+      }
+      if (GRAD_ONLY) {
+        acc += g0 * C.dl[2 * f] + g1 * C.dl[2 * f + 1];
+      } else {
+        double* hd = C.H + (2 * f) * ldh + 2 * f;
+        hd[0] = d00;
+        hd[1] = d01;
+        hd[ldh] = d01;
+        hd[ldh + 1] = d11;
+        C.g[2 * f] = g0;
+        C.g[2 * f + 1] = g1;
+        if (first) {
+          C.S[2 * f] = 1.0 / (1.0 + sqrt(d00));
+          C.S[2 * f + 1] = 1.0 / (1.0 + sqrt(d11));
+        }
+        const double x0 = C.x[2 * l], x1 = C.x[2 * l + 1];
+        const double p0 = fmin(fmax(x0 - g0, -K.bound), K.bound), p1 = fmin(fmax(x1 - g1, -K.bound), K.bound);
+        gmax = fmax(gmax, fmax(fabs(x0 - p0), fabs(x1 - p1)));
       }
     }
-    if (grad_only) {
-      acc += g0 * C.dl[2 * f] + g1 * C.dl[2 * f + 1];
-    } else {
-      double* hd = C.H + (2 * f) * ldh + 2 * f;
-      hd[0] = d00;
-      hd[1] = d01;
-      hd[ldh] = d01;
-      hd[ldh + 1] = d11;
-      C.g[2 * f] = g0;
-      C.g[2 * f + 1] = g1;
-      if (first) {
-        C.S[2 * f] = 1.0 / (1.0 + sqrt(d00));
-        C.S[2 * f + 1] = 1.0 / (1.0 + sqrt(d11));
+  } else {
+    // serial path for inputs without clean edge twins: one lane accumulates every edge in order
+    if (C.lane == 0) {
+      for (int i = 0; i < C.n; ++i) C.g[i] = 0.0;
+      for (int e = 0; e < C.Ec; ++e) {
+        const uint32_t mt = C.meta[e];
+        const int fs = C.freeof[mt & 0xfff], fd = C.freeof[(mt >> 12) & 0xfff];
+        const double a = C.scr[e], r0 = C.scr[E + e], r1 = C.scr[2 * E + e];
+        const double m00 = C.scr[3 * E + e], m01 = C.scr[4 * E + e], m10 = C.scr[5 * E + e],
+                     m11 = C.scr[6 * E + e];
+        if (fs >= 0) {
+          C.g[2 * fs] -= a * (m00 * r0 + m10 * r1);
+          C.g[2 * fs + 1] -= a * (m01 * r0 + m11 * r1);
+          if (!GRAD_ONLY) {
+            double* hd = C.H + (2 * fs) * ldh + 2 * fs;
+            hd[0] += a * (m00 * m00 + m10 * m10);
+            hd[1] += a * (m00 * m01 + m10 * m11);
+            hd[ldh] += a * (m00 * m01 + m10 * m11);
+            hd[ldh + 1] += a * (m01 * m01 + m11 * m11);
+          }
+        }
+        if (fd >= 0) {
+          C.g[2 * fd] += a * r0;
+          C.g[2 * fd + 1] += a * r1;
+          if (!GRAD_ONLY) {
+            C.H[(2 * fd) * ldh + 2 * fd] += a;
+            C.H[(2 * fd + 1) * ldh + 2 * fd + 1] += a;
+          }
+        }
+        if (!GRAD_ONLY && fs >= 0 && fd >= 0) {
+          double* h0 = C.H + (2 * fs) * ldh + 2 * fd;
+          double* h1 = C.H + (2 * fd) * ldh + 2 * fs;
+          h0[0] -= a * m00; h0[1] -= a * m10; h0[ldh] -= a * m01; h0[ldh + 1] -= a * m11;
+          h1[0] -= a * m00; h1[1] -= a * m01; h1[ldh] -= a * m10; h1[ldh + 1] -= a * m11;
+        }
       }
-      const double x0 = C.x[2 * l], x1 = C.x[2 * l + 1];
-      const double p0 = fmin(fmax(x0 - g0, -K.bound), K.bound), p1 = fmin(fmax(x1 - g1, -K.bound), K.bound);
-      gmax = fmax(gmax, fmax(fabs(x0 - p0), fabs(x1 - p1)));
+    }
+    __syncwarp();
+    for (int i = C.lane; i < C.n; i += 32) {
+      if (GRAD_ONLY) {
+        acc += C.g[i] * C.dl[i];
+      } else {
+        if (first) C.S[i] = 1.0 / (1.0 + sqrt(C.H[i * ldh + i]));
+        const int l = C.lof[i >> 1];
+        const double xi = C.x[2 * l + (i & 1)];
+        const double p = fmin(fmax(xi - C.g[i], -K.bound), K.bound);
+        gmax = fmax(gmax, fabs(xi - p));
+      }
     }
   }
   __syncwarp();
-  if (grad_only) return warp_sum(acc);
+  if (GRAD_ONLY) return warp_sum(acc);
   return warp_max(gmax);
 }
 
@@ -458,9 +453,8 @@ __device__ __forceinline__ bool lm_step2(const Warp2Ctx& C, double radius, const
   return ok && finite;
 }
 
-__device__ __noinline__ CandNorms make_candidate2(const Warp2Ctx& C, double alpha, const DevConsts& K) {
+__device__ __forceinline__ CandNorms make_candidate2(const Warp2Ctx& C, double alpha, const DevConsts& K) {
   CandNorms nr{0.0, 0.0};
-#pragma unroll 1
   for (int i = C.lane; i < 2 * C.Nc; i += 32) {
     const int f = C.freeof[i >> 1];
     const double xv = C.x[i];
@@ -641,8 +635,7 @@ __device__ __forceinline__ void warp_setup(Ctx& C, uint32_t* rowstart, uint32_t*
 
 template <int WARPS, int NREG>
 __global__ void __launch_bounds__(WARPS * 32, (NREG > 16 ? 8 : 12) / WARPS)
-solve_warp2_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ DevConsts K,
-                   const __grid_constant__ WarpBucket B) {
+solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t item = blockIdx.x * WARPS + wib;
@@ -713,9 +706,9 @@ solve_warp2_kernel(const __grid_constant__ DevProblem P, const __grid_constant__
   LFR_TICK(cyc_setup);
 
   // ---- iteration 0 -----------------------------------------------------------------
-  double cost = eval_pass2(C, C.x, K, 0, nullptr, nullptr);
+  double cost = eval_pass2<false, false>(C, C.x, K);
   LFR_TICK(cyc_eval);
-  double gmax = assemble2(C, true, false, K);
+  double gmax = assemble2<false>(C, true, K);
   LFR_TICK(cyc_asm);
   const double cost0 = cost;
   double radius = K.radius0, nu = 2.0;
@@ -754,7 +747,7 @@ solve_warp2_kernel(const __grid_constant__ DevProblem P, const __grid_constant__
     n_invalid = 0;
     // projected Armijo line search along dl (bounds-constrained problem, A.7b)
     CandNorms nr = make_candidate2(C, 1.0, K);
-    double cost_c = eval_pass2(C, C.xc, K, kEvalNorms, nullptr, &nr);
+    double cost_c = eval_pass2<false, true>(C, C.xc, K, nullptr, &nr);
     LFR_TICK(cyc_eval);
     bool c_valid = isfinite(cost_c);
     if (!c_valid || cost_c > cost + K.ls_suff * gd * 1.0) {
@@ -762,7 +755,7 @@ solve_warp2_kernel(const __grid_constant__ DevProblem P, const __grid_constant__
       LsSample previous{0.0, 0.0, 0.0, false, false};
       LsSample current{1.0, cost_c, 0.0, c_valid, false};
       if (c_valid) {
-        current.gradient = assemble2(C, false, true, K);
+        current.gradient = assemble2<true>(C, false, K);
         current.gradient_valid = isfinite(current.gradient);
       }
       int ls_iter = 0;
@@ -778,7 +771,7 @@ solve_warp2_kernel(const __grid_constant__ DevProblem P, const __grid_constant__
         previous = current;
         nr = make_candidate2(C, step, K);
         double dphi;
-        cost_c = eval_pass2(C, C.xc, K, kEvalDirDeriv | kEvalNorms, &dphi, &nr);
+        cost_c = eval_pass2<true, true>(C, C.xc, K, &dphi, &nr);
         c_valid = isfinite(cost_c);
         current = LsSample{step, cost_c, 0.0, c_valid, false};
         if (c_valid) {
@@ -792,7 +785,7 @@ solve_warp2_kernel(const __grid_constant__ DevProblem P, const __grid_constant__
         __syncwarp();
       } else {  // line search failed: delta unchanged, candidate = P(x + delta)
         nr = make_candidate2(C, 1.0, K);
-        cost_c = eval_pass2(C, C.xc, K, kEvalNorms, nullptr, &nr);
+        cost_c = eval_pass2<false, true>(C, C.xc, K, nullptr, &nr);
         c_valid = isfinite(cost_c);
       }
     }
@@ -806,7 +799,7 @@ solve_warp2_kernel(const __grid_constant__ DevProblem P, const __grid_constant__
       __syncwarp();
       cost = cost_c;
       LFR_TICK(cyc_ls);
-      gmax = assemble2(C, false, false, K);
+      gmax = assemble2<false>(C, false, K);
       x_norm = sqrt(nr.xn2);
       LFR_TICK(cyc_asm);
       success = true;

@@ -405,7 +405,8 @@ def build_problem_native(ms: MatchSet, banned_images=(), log=None) -> Problem:
                     ("n_images_seen", C.c_uint32), ("max_track_size", C.c_uint32), ("max_component_size", C.c_uint32),
                     ("n_meta_components", C.c_uint32), ("n_oversized_meta_components", C.c_uint32),
                     ("n_cut_groups", C.c_uint32), ("reserved", C.c_uint32), ("n_edges", C.c_uint64),
-                    ("tracks_ms", C.c_double), ("graph_cut_ms", C.c_double)]
+                    ("tracks_ms", C.c_double), ("graph_cut_ms", C.c_double), ("graph_ms", C.c_double),
+                    ("dispatch_ms", C.c_double)]
 
     L = load_host()
     L.lfr_host_stage_create.argtypes = [C.POINTER(HostInput), C.POINTER(C.c_void_p), C.POINTER(HostSizes)]
@@ -467,7 +468,8 @@ def build_problem_native(ms: MatchSet, banned_images=(), log=None) -> Problem:
     say("# components: %d" % Cn)
     say("max component size: %d" % sz.max_component_size)
     info.update(n_tracks=int(sz.n_tracks), n_components=Cn, max_component_size=int(sz.max_component_size),
-                tracks_ms=float(sz.tracks_ms), graph_cut_ms=float(sz.graph_cut_ms),
+                tracks_ms=float(sz.tracks_ms), graph_cut_ms=float(sz.graph_cut_ms), graph_ms=float(sz.graph_ms),
+                dispatch_ms=float(sz.dispatch_ms),
                 n_meta_components=int(sz.n_meta_components),
                 n_oversized_meta_components=int(sz.n_oversized_meta_components), n_cut_groups=int(sz.n_cut_groups),
                 host_stage="native")

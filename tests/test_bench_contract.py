@@ -18,7 +18,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 2 and d["vs_baseline"] is None
     assert d["dtype"] == "f64" and d["data"] == "synthetic" and "workload" in d["config"]
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # "reference" when oracle/_ref/solve_O2 (the reference's solve.cc compiled against the shims) exists, else the oracle port
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == ("reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "solve_O2")) else "port")
+    assert set(d["config"]) >= {"workload", "nodes", "directed_edges", "tracks_refined", "per_gpu", "l2"}
+    # the reference arm must not map the product library
+    assert "liblfr_b200" not in r.stderr
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
