@@ -329,6 +329,65 @@ def run_reference(args):
     return 0
 
 
+def sharded_record(lib, world, args):
+    """BASELINE.json configs[3] (cfg4, N <= 4) / configs[4] (cfg5, N = 8): ONE scene whose components
+    are LPT-packed over the N GPUs by lfr_solve_multi() (include/lfr.h) — one C-ABI call from one
+    process, page-locked host arrays, every device pulling only its own components' edge records and
+    writing its results straight back: no data-path collective, nothing to gather.  Timed against the
+    same call on one device (strong scaling)."""
+    import ctypes as C
+    import torch
+    from lfr_b200 import build_problem, refined_track_count, synth
+    from lfr_b200.capi import LfrMultiInfo
+    name = os.environ.get("LFR_BENCH_SHARDED_WORKLOAD") or ("cfg4" if world <= 4 else "cfg5")
+    t0 = time.perf_counter()
+    p = build_problem(synth.generate(name))
+    t_build = time.perf_counter() - t0
+    n_tracks = refined_track_count(p)
+    s2, keep, pos_pinned, h2d = pinned_problem(lib, p)
+    opts = lib.default_options()
+    stt, bufs = lib.make_stats(p.n_components)
+
+    def run(devices, reps):
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        info = LfrMultiInfo()
+        wall, kern = [], []
+        for i in range(2 + reps):
+            pos_pinned.zero_()
+            for d in devices:
+                torch.cuda.synchronize(d)
+            t1 = time.perf_counter()
+            rc = lib.lib.lfr_solve_multi(C.byref(s2), C.byref(opts), dev.ctypes.data, len(devices),
+                                         pos_pinned.data_ptr(), C.byref(stt), C.byref(info))
+            dt = time.perf_counter() - t1
+            lib.check(rc, "lfr_solve_multi")
+            if i >= 2:
+                wall.append(dt)
+                kern.append(list(info.kernel_ms)[:len(devices)])
+        pos = pos_pinned.numpy()[:2 * p.graph.n_nodes].copy()
+        return 1e3 * float(np.median(wall)), np.median(np.array(kern), axis=0), pos, info, bufs["iterations"].copy()
+
+    reps = 5
+    ms1, k1, pos1, _, it1 = run([0], reps)
+    msN, kN, posN, info, itN = run(list(range(world)), reps)
+    sizes = np.diff(p.comp_ptr.astype(np.int64))
+    return {
+        "workload": WORKLOADS.get(name, name), "n_gpus": world, "api": "lfr_solve_multi() (include/lfr.h), page-locked host arrays",
+        "nodes": int(p.graph.n_nodes), "directed_edges": int(p.graph.n_edges), "components_solved": int((sizes > 1).sum()),
+        "max_component_nodes": int(sizes.max()), "tracks_refined": int(n_tracks),
+        "one_gpu": {"ms_per_solve": ms1, "kernel_ms": float(k1[0]), "tracks_per_s": n_tracks / (ms1 / 1e3)},
+        "n_gpu": {"ms_per_solve": msN, "kernel_ms_max": float(np.max(kN)), "kernel_ms_per_device": [float(x) for x in kN],
+                  "tracks_per_s": n_tracks / (msN / 1e3), "components_per_device": list(info.n_slots)[:world],
+                  "edges_per_device": list(info.n_edges)[:world], "zero_copy": int(info.zero_copy)},
+        "strong_scaling_efficiency": ms1 / (world * msN),
+        "strong_scaling_efficiency_kernels": float(k1[0]) / (world * float(np.max(kN))),
+        "gather_ms": 0.0, "collective": "none: components never span devices; results are written straight into the caller's page-locked array",
+        "bitwise_identical_to_one_gpu": bool(np.array_equal(pos1, posN) and np.array_equal(it1, itN)),
+        "timing": "host wall clock around the call, median of %d (2 warm-up calls)" % reps,
+        "scene_build_s": t_build, "h2d_bytes_if_copied": int(h2d),
+    }
+
+
 def run_b200(args):
     import ctypes as C
     import torch
@@ -419,6 +478,15 @@ def run_b200(args):
         c = torch.tensor([n_tracks, tot_iters, alg_bytes], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         tot_tracks, tot_iters, tot_alg = int(c[0]), int(c[1]), int(c[2])
+    # ---- N > 1: the PARTITION path (north star: components of ONE scene partitioned across the GPUs) --
+    sharded = None
+    if world > 1 and os.environ.get("LFR_BENCH_SHARDED", "1") != "0":
+        if rank == 0:
+            try:
+                sharded = sharded_record(lib, world, args)
+            except Exception as e:   # never lose the main line over the extra record
+                sharded = {"error": repr(e)[:300]}
+        dist.barrier()               # the other ranks idle while rank 0 drives all N devices through one C-ABI call
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -490,6 +558,8 @@ def run_b200(args):
                         "host_stage": "csrc/lfr_host.cc, single-threaded C++ (same stage feeds both)"},
         "clocks": clocks,
     }
+    if sharded is not None:
+        line["sharded"] = sharded
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -167,6 +167,29 @@ void lfr_options_default(lfr_options* o);
 int lfr_solve(const lfr_problem* p, const lfr_options* o, double* positions,
               lfr_stats* stats);
 
+/*
+ * The same solve on several GPUs of one node from ONE call ("one call drives
+ * 1..8 GPUs").  Components are independent (solve.cc:123-125 drops cross-component edges,
+ * solve.cc:586 caps a component at #images nodes), so the dispatch slots are LPT-packed over
+ * `devices` by directed-edge count — the reference's largest-first queue (solve.cc:599-604) spread
+ * over devices — and every device solves its slots concurrently.  With page-locked `p->edges` /
+ * `positions` each device pulls only ITS components' edge records from the shared host array and
+ * writes its results straight back (disjoint entries): the edge data is partitioned without being
+ * copied or replicated and no collective is needed; the small per-node arrays are replicated.
+ * Pageable buffers go through each device's HBM (edges replicated) and are merged on the host.
+ * Results are bitwise identical to lfr_solve() on one device.  `info` may be NULL.
+ * The oracle exports the symbol and ignores `devices`.
+ */
+typedef struct lfr_multi_info {
+  double kernel_ms[16], total_ms[16];  /* per entry of `devices`                               */
+  uint32_t n_slots[16];                /* components solved by that device                     */
+  uint64_t n_edges[16];                /* their directed edges (the LPT weight)                */
+  int32_t zero_copy, reserved;
+} lfr_multi_info;
+
+int lfr_solve_multi(const lfr_problem* p, const lfr_options* o, const int32_t* devices, int32_t n_devices,
+                    double* positions, lfr_stats* stats, lfr_multi_info* info);
+
 /* ---- device-resident plan (b200 only; the oracle returns LFR_EUNSUPPORTED) --
  * lfr_plan_create copies the problem to HBM once; lfr_plan_solve re-runs the
  * whole solve from the stored initial positions, asynchronously on `stream`

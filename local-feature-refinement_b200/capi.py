@@ -64,9 +64,14 @@ class LfrStats(C.Structure):
     ]
 
 
+class LfrMultiInfo(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double * 16), ("total_ms", C.c_double * 16), ("n_slots", C.c_uint32 * 16),
+                ("n_edges", C.c_uint64 * 16), ("zero_copy", C.c_int32), ("reserved", C.c_int32)]
+
+
 #: every symbol include/lfr.h declares
 ABI_SYMBOLS = [
-    "lfr_abi_version", "lfr_backend", "lfr_last_error", "lfr_options_default", "lfr_solve",
+    "lfr_abi_version", "lfr_backend", "lfr_last_error", "lfr_options_default", "lfr_solve", "lfr_solve_multi",
     "lfr_plan_create", "lfr_plan_solve", "lfr_plan_download", "lfr_plan_num_launches",
     "lfr_plan_traffic", "lfr_plan_destroy", "lfr_debug_edge_eval",
 ]
@@ -94,6 +99,9 @@ class Library:
         L.lfr_options_default.restype = None
         L.lfr_solve.argtypes = [C.POINTER(LfrProblem), C.POINTER(LfrOptions), C.c_void_p, C.POINTER(LfrStats)]
         L.lfr_solve.restype = C.c_int
+        L.lfr_solve_multi.argtypes = [C.POINTER(LfrProblem), C.POINTER(LfrOptions), C.c_void_p, C.c_int32, C.c_void_p,
+                                      C.POINTER(LfrStats), C.POINTER(LfrMultiInfo)]
+        L.lfr_solve_multi.restype = C.c_int
         L.lfr_plan_create.argtypes = [C.POINTER(LfrProblem), C.POINTER(LfrOptions), C.c_void_p,
                                       C.POINTER(C.c_void_p)]
         L.lfr_plan_create.restype = C.c_int
@@ -187,6 +195,42 @@ class Library:
         self.check(rc, "lfr_solve")
         del keep
         return pos, self.stats_dict(st, bufs)
+
+    def solve_multi(self, p: Problem, devices, options: Optional[LfrOptions] = None,
+                    positions: Optional[np.ndarray] = None, pinned: bool = False):
+        """lfr_solve_multi: one call, several GPUs.  pinned=True page-locks the edge array and the
+        position array first (torch), which lets every device pull only its own components' edges.
+        Returns (positions [N,2], stats dict incl. per-device `multi` info)."""
+        s, keep = self.marshal(p)
+        o = options if options is not None else self.default_options()
+        N = p.graph.n_nodes
+        pos = np.zeros((N, 2), dtype=np.float64) if positions is None else \
+            np.ascontiguousarray(positions, dtype=np.float64).reshape(N, 2).copy()
+        holders = []
+        pos_ptr = _ptr(pos)
+        if pinned:
+            import torch
+            e_pin = torch.empty(max(keep["edges"].nbytes, 16), dtype=torch.uint8).pin_memory()
+            e_pin.numpy()[:keep["edges"].nbytes] = keep["edges"].view(np.uint8).reshape(-1)
+            s.edges = e_pin.data_ptr()
+            p_pin = torch.zeros(max(2 * N, 2), dtype=torch.float64).pin_memory()
+            p_pin.numpy()[:2 * N] = pos.reshape(-1)
+            pos_ptr = p_pin.data_ptr()
+            holders = [e_pin, p_pin]
+        dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+        st, bufs = self.make_stats(p.n_components)
+        info = LfrMultiInfo()
+        rc = self.lib.lfr_solve_multi(C.byref(s), C.byref(o), dev.ctypes.data, int(dev.shape[0]), pos_ptr,
+                                      C.byref(st), C.byref(info))
+        self.check(rc, "lfr_solve_multi")
+        if pinned:
+            pos = holders[1].numpy()[:2 * N].reshape(N, 2).copy()
+        d = self.stats_dict(st, bufs)
+        n = int(dev.shape[0])
+        d["multi"] = dict(devices=dev.tolist(), kernel_ms=list(info.kernel_ms)[:n], total_ms=list(info.total_ms)[:n],
+                          n_slots=list(info.n_slots)[:n], n_edges=list(info.n_edges)[:n], zero_copy=int(info.zero_copy))
+        del keep, holders
+        return pos, d
 
     def edge_eval(self, edges: np.ndarray, kind: np.ndarray, xs: np.ndarray, xd: np.ndarray,
                   options: Optional[LfrOptions] = None):

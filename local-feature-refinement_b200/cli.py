@@ -9,7 +9,7 @@ command-line error, solve.cc:397-401; -1 = 255 when the input does not parse or
 the output cannot be written, solve.cc:433-436,674-677), so
 local-feature-evaluation/benchmark.py:100-104, eth/benchmark.py:108-112 and
 custom_demo.py:101-105 run unchanged.  `--n_threads` is accepted and ignored
-(the solve runs on the GPU).  Opt-in extras: --device, --gpus, --stats_json.
+(the solve runs on the GPU).  Opt-in extras: --device, --gpus N (one process drives N GPUs), --stats_json.
 """
 from __future__ import annotations
 
@@ -118,12 +118,6 @@ def parse_args(argv):
 
 def main(argv=None) -> int:
     args = parse_args(sys.argv[1:] if argv is None else argv)
-    if args.gpus > 1 and "RANK" not in os.environ:
-        # one process per GPU: re-launch under torch.distributed.run (NCCL over NVLink)
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
-               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000),
-               os.path.abspath(__file__)] + list(sys.argv[1:] if argv is None else argv)
-        return subprocess.call(cmd)
 
     from . import wire
     from .solver import refine
@@ -160,8 +154,12 @@ def main(argv=None) -> int:
     def solve_fn(p):
         t1 = time.perf_counter()
         if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            from .dist import solve_distributed
+            from .dist import solve_distributed       # launched under torchrun: one rank per GPU
             pos, st = solve_distributed(p)
+        elif args.gpus > 1:
+            # one call drives the GPUs (lfr_solve_multi, include/lfr.h): components LPT-packed over the
+            # devices, each pulling only its own edge records from the page-locked arrays
+            pos, st = lib.solve_multi(p, range(args.gpus), opts, pinned=True)
         else:
             from .solver import solve_problem
             pos, st = solve_problem(p, opts)

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "lfr_solve_cta.cuh"
@@ -163,6 +165,8 @@ struct lfr_plan {
   // pinned positions directly (device-side addresses of those host buffers), nullptr = through HBM
   const float4* zc_edges = nullptr;
   double* zc_positions = nullptr;
+  const uint8_t* slot_owner = nullptr;  // lfr_solve_multi(): owner[c] of every dispatch slot, this plan solves owner == owner_id
+  uint8_t owner_id = 0;
   bool edges_in_hbm = false;       // the edge array was (or is being) copied to `edges`
   bool needs_hbm_edges = false;    // some bucket (smem-Cholesky warp tier, CTA tier) reads edges from global memory
   cudaStream_t copy_stream = nullptr;
@@ -264,6 +268,7 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
     const uint32_t nc = end - beg;
     pl->comp_size[c] = nc;
     if (nc <= 1) continue;  // solve.cc:619-622
+    if (pl->slot_owner && pl->slot_owner[c] != pl->owner_id) continue;  // another device's component
     ++pl->n_solved;
     uint64_t eup = 0;
     uint32_t nfree = 0;
@@ -557,10 +562,10 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
 }
 
 int set_kernel_attrs() {
-  static thread_local int done_for_device = -1;
+  static bool done_for_device[16] = {};  // per device, guarded by that device's workspace mutex / idempotent otherwise
   int dev = 0;
   LFR_CUDA(cudaGetDevice(&dev));
-  if (done_for_device == dev) return LFR_OK;
+  if (dev >= 0 && dev < 16 && done_for_device[dev]) return LFR_OK;
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -583,7 +588,7 @@ int set_kernel_attrs() {
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_tile_kernel<128, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
-  done_for_device = dev;
+  if (dev >= 0 && dev < 16) done_for_device[dev] = true;
   return LFR_OK;
 }
 
@@ -746,7 +751,64 @@ struct DeviceWorkspace {
   bool ready = false;
 };
 constexpr int kMaxDevices = 16;
-thread_local DeviceWorkspace g_ws[kMaxDevices];
+DeviceWorkspace g_ws[kMaxDevices];
+std::mutex g_ws_mutex[kMaxDevices];  // one solve at a time per device workspace; distinct devices run concurrently
+
+int ensure_workspace(int device) {
+  DeviceWorkspace& ws = g_ws[device];
+  if (ws.ready) return LFR_OK;
+  LFR_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) LFR_CUDA(cudaEventCreate(&ws.ev[i]));
+  ws.plan = new lfr_plan();
+  ws.plan->device = device;
+  ws.ready = true;
+  return LFR_OK;
+}
+
+// One device's part of a solve: uploads, launches, results.  `slot_owner` / `owner_id` restrict the
+// plan to the dispatch slots this device owns (nullptr = all).  Caller holds g_ws_mutex[device].
+int solve_on_device(const lfr_problem* p, const lfr_options& o, double* positions, lfr_stats* st,
+                    const uint8_t* slot_owner, uint8_t owner_id, double* pos_scratch) {
+  LFR_TRY(select_device(o));
+  LFR_TRY(ensure_workspace(o.device));
+  DeviceWorkspace& ws = g_ws[o.device];
+  lfr_plan* pl = ws.plan;
+  cudaStream_t s = ws.stream;
+  pl->slot_owner = slot_owner;
+  pl->owner_id = owner_id;
+  // page-locked caller buffers are used in place (see include/lfr.h); pageable ones go through HBM
+  const bool zero_copy = !(o.debug_flags & LFR_DBG_NO_ZERO_COPY);
+  const float4* zc_edges = (zero_copy && p->n_edges) ? static_cast<const float4*>(device_view_of_pinned(p->edges)) : nullptr;
+  double* zc_positions = (zero_copy && p->n_nodes) ? static_cast<double*>(device_view_of_pinned(positions)) : nullptr;
+  LFR_CUDA(cudaEventRecord(ws.ev[0], s));
+  LFR_TRY(fill_plan(pl, p, o, positions, s, /*stage_positions_directly=*/true, zc_edges, zc_positions));
+  LFR_CUDA(cudaEventRecord(ws.ev[1], s));
+  LFR_TRY(launch_solve(pl, s));
+  LFR_CUDA(cudaEventRecord(ws.ev[2], s));
+  // several devices, pageable positions: each device returns its copy into its own scratch array
+  // and the caller merges the entries of the components it owns
+  int rc = download(pl, s, (slot_owner && !zc_positions) ? pos_scratch : positions, st);
+  if (pl->copy_stream && pl->zc_edges && pl->edges_in_hbm) {
+    // the bulk copy reads the caller's buffer: it must be over before the call returns
+    cudaError_t e = cudaStreamSynchronize(pl->copy_stream);
+    if (e != cudaSuccess && rc == LFR_OK) rc = fail(cuda_code(e), cudaGetErrorString(e));
+  }
+  pl->slot_owner = nullptr;
+  if (rc) return rc;
+  LFR_CUDA(cudaEventRecord(ws.ev[3], s));
+  LFR_CUDA(cudaEventSynchronize(ws.ev[3]));
+  if (st) {
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]);
+    cudaEventElapsedTime(&b, ws.ev[1], ws.ev[2]);
+    cudaEventElapsedTime(&c, ws.ev[2], ws.ev[3]);
+    st->h2d_ms = a;     // uploads of the arrays that go through HBM (+ schedule)
+    st->kernel_ms = b;  // the solve kernels (with zero-copy: including their PCIe pulls)
+    st->d2h_ms = c;
+    st->total_ms = (double)a + b + c;
+  }
+  return LFR_OK;
+}
 
 }  // namespace
 
@@ -888,45 +950,139 @@ int lfr_solve(const lfr_problem* p, const lfr_options* opt, double* positions, l
   if (p->n_nodes && !positions) return fail(LFR_EINVAL, "positions is NULL");
   lfr_options o;
   if (opt) o = *opt; else lfr_options_default(&o);
-  LFR_TRY(select_device(o));
-  if (o.device >= kMaxDevices) return fail(LFR_EUNSUPPORTED, "device ordinal >= 16");
-  DeviceWorkspace& ws = g_ws[o.device];
-  if (!ws.ready) {
-    LFR_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) LFR_CUDA(cudaEventCreate(&ws.ev[i]));
-    ws.plan = new lfr_plan();
-    ws.plan->device = o.device;
-    ws.ready = true;
+  if (o.device < 0 || o.device >= kMaxDevices) return fail(LFR_EUNSUPPORTED, "device ordinal out of [0, 16)");
+  std::lock_guard<std::mutex> lock(g_ws_mutex[o.device]);
+  return solve_on_device(p, o, positions, st, nullptr, 0, nullptr);
+}
+
+int lfr_solve_multi(const lfr_problem* p, const lfr_options* opt, const int32_t* devices, int32_t n_devices,
+                    double* positions, lfr_stats* st, lfr_multi_info* info) {
+  LFR_TRY(validate(p));
+  if (p->n_nodes && !positions) return fail(LFR_EINVAL, "positions is NULL");
+  if (!devices || n_devices < 1 || n_devices > kMaxDevices) return fail(LFR_EINVAL, "devices: need 1..16 device ordinals");
+  for (int d = 0; d < n_devices; ++d) {
+    if (devices[d] < 0 || devices[d] >= kMaxDevices) return fail(LFR_EUNSUPPORTED, "device ordinal out of [0, 16)");
+    for (int e = 0; e < d; ++e)
+      if (devices[e] == devices[d]) return fail(LFR_EINVAL, "devices: duplicate ordinal");
   }
-  lfr_plan* pl = ws.plan;
-  cudaStream_t s = ws.stream;
-  // page-locked caller buffers are used in place (see include/lfr.h); pageable ones go through HBM
-  const bool zero_copy = !(o.debug_flags & LFR_DBG_NO_ZERO_COPY);
-  const float4* zc_edges = (zero_copy && p->n_edges) ? static_cast<const float4*>(device_view_of_pinned(p->edges)) : nullptr;
-  double* zc_positions = (zero_copy && p->n_nodes) ? static_cast<double*>(device_view_of_pinned(positions)) : nullptr;
-  LFR_CUDA(cudaEventRecord(ws.ev[0], s));
-  LFR_TRY(fill_plan(pl, p, o, positions, s, /*stage_positions_directly=*/true, zc_edges, zc_positions));
-  LFR_CUDA(cudaEventRecord(ws.ev[1], s));
-  LFR_TRY(launch_solve(pl, s));
-  LFR_CUDA(cudaEventRecord(ws.ev[2], s));
-  int rc = download(pl, s, positions, st);
-  if (pl->copy_stream && pl->zc_edges && pl->edges_in_hbm) {
-    // the bulk copy reads the caller's buffer: it must be over before the call returns
-    cudaError_t e = cudaStreamSynchronize(pl->copy_stream);
-    if (e != cudaSuccess && rc == LFR_OK) rc = fail(cuda_code(e), cudaGetErrorString(e));
+  lfr_options o0;
+  if (opt) o0 = *opt; else lfr_options_default(&o0);
+  const uint32_t C = p->n_components;
+  // ---- LPT packing of the dispatch slots by directed-edge count, largest first (the reference's
+  // largest-first queue, solve.cc:599-604, spread over devices); deterministic
+  std::vector<uint64_t> weight(C, 0);
+  const uint32_t total_slots = C ? p->comp_ptr[C] : 0;
+  for (uint32_t c = 0; c < C; ++c) {
+    const uint32_t beg = p->comp_ptr[c], end = p->comp_ptr[c + 1];
+    if (end < beg || end > total_slots) return fail(LFR_EINVAL, "comp_ptr not monotone");
+    if (end - beg <= 1) continue;
+    for (uint32_t i = beg; i < end; ++i) {
+      const uint32_t v = p->comp_nodes[i];
+      if (v >= p->n_nodes) return fail(LFR_EINVAL, "comp_nodes out of range");
+      weight[c] += p->row_ptr[v + 1] - p->row_ptr[v];
+    }
   }
-  if (rc) return rc;
-  LFR_CUDA(cudaEventRecord(ws.ev[3], s));
-  LFR_CUDA(cudaEventSynchronize(ws.ev[3]));
+  std::vector<uint32_t> order(C);
+  for (uint32_t c = 0; c < C; ++c) order[c] = c;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+  std::vector<uint8_t> owner(C, 0);
+  std::vector<uint64_t> load(n_devices, 0);
+  std::vector<uint32_t> n_slots(n_devices, 0);
+  for (uint32_t c : order) {
+    int best = 0;
+    for (int d = 1; d < n_devices; ++d)
+      if (load[d] < load[best]) best = d;
+    owner[c] = (uint8_t)best;
+    load[best] += weight[c];
+    if (weight[c]) ++n_slots[best];
+  }
+  // ---- one host thread per device: upload the (small) per-node arrays, launch, collect.  With
+  // page-locked caller buffers every device pulls only ITS components' edge records from the shared
+  // host array and writes its results straight into `positions` (disjoint entries): the edge data is
+  // partitioned without ever being copied, and no collective is needed.
+  std::vector<lfr_stats> dst(n_devices);
+  std::vector<std::vector<int32_t>> d_iter(n_devices), d_term(n_devices);
+  std::vector<std::vector<double>> d_c0(n_devices), d_c1(n_devices), d_pos(n_devices);
+  std::vector<int> rcs(n_devices, LFR_OK);
+  std::vector<std::string> errs(n_devices);
+  const bool pos_pinned = !(o0.debug_flags & LFR_DBG_NO_ZERO_COPY) && p->n_nodes && device_view_of_pinned(positions) != nullptr;
+  auto work = [&](int d) {
+    lfr_options o = o0;
+    o.device = devices[d];
+    std::memset(&dst[d], 0, sizeof(lfr_stats));
+    d_iter[d].assign(C, 0);
+    d_term[d].assign(C, 0);
+    d_c0[d].assign(C, 0.0);
+    d_c1[d].assign(C, 0.0);
+    dst[d].iterations = d_iter[d].data();
+    dst[d].termination = d_term[d].data();
+    dst[d].initial_cost = d_c0[d].data();
+    dst[d].final_cost = d_c1[d].data();
+    if (!pos_pinned) d_pos[d].assign(2 * (size_t)p->n_nodes, 0.0);
+    std::lock_guard<std::mutex> lock(g_ws_mutex[o.device]);
+    rcs[d] = solve_on_device(p, o, positions, &dst[d], owner.data(), (uint8_t)d, pos_pinned ? nullptr : d_pos[d].data());
+    if (rcs[d]) errs[d] = g_last_error;
+  };
+  if (n_devices == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> threads;
+    for (int d = 0; d < n_devices; ++d) threads.emplace_back(work, d);
+    for (auto& t : threads) t.join();
+  }
+  for (int d = 0; d < n_devices; ++d)
+    if (rcs[d]) return fail(rcs[d], "device " + std::to_string(devices[d]) + ": " + errs[d]);
+  // ---- merge by owner
+  if (!pos_pinned) {
+    for (uint32_t c = 0; c < C; ++c) {
+      const uint32_t beg = p->comp_ptr[c], end = p->comp_ptr[c + 1];
+      if (end - beg <= 1) continue;
+      const double* src = d_pos[owner[c]].data();
+      for (uint32_t i = beg; i < end; ++i) {
+        const size_t v = p->comp_nodes[i];
+        positions[2 * v] = src[2 * v];
+        positions[2 * v + 1] = src[2 * v + 1];
+      }
+    }
+  }
   if (st) {
-    float a = 0, b = 0, c = 0;
-    cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]);
-    cudaEventElapsedTime(&b, ws.ev[1], ws.ev[2]);
-    cudaEventElapsedTime(&c, ws.ev[2], ws.ev[3]);
-    st->h2d_ms = a;     // uploads of the arrays that go through HBM (+ schedule)
-    st->kernel_ms = b;  // the solve kernels (with zero-copy: including their PCIe pulls)
-    st->d2h_ms = c;
-    st->total_ms = (double)a + b + c;
+    uint64_t ti = 0, tl = 0;
+    uint32_t ns = 0, nk = 0;
+    double h = 0, k = 0, dd = 0, tt = 0;
+    for (int d = 0; d < n_devices; ++d) {
+      ti += dst[d].total_iterations;
+      tl += dst[d].total_line_search_steps;
+      ns += dst[d].n_solved;
+      nk += dst[d].n_kernel_launches;
+      h = std::max(h, dst[d].h2d_ms);
+      k = std::max(k, dst[d].kernel_ms);
+      dd = std::max(dd, dst[d].d2h_ms);
+      tt = std::max(tt, dst[d].total_ms);
+    }
+    for (uint32_t c = 0; c < C; ++c) {
+      const int d = owner[c];
+      if (st->iterations) st->iterations[c] = d_iter[d][c];
+      if (st->termination) st->termination[c] = d_term[d][c];
+      if (st->initial_cost) st->initial_cost[c] = d_c0[d][c];
+      if (st->final_cost) st->final_cost[c] = d_c1[d][c];
+    }
+    st->total_iterations = ti;
+    st->total_line_search_steps = tl;
+    st->n_solved = ns;
+    st->n_kernel_launches = nk;
+    st->h2d_ms = h;       // maxima over the devices (they run concurrently)
+    st->kernel_ms = k;
+    st->d2h_ms = dd;
+    st->total_ms = tt;
+  }
+  if (info) {
+    for (int d = 0; d < n_devices && d < 16; ++d) {
+      info->kernel_ms[d] = dst[d].kernel_ms;
+      info->total_ms[d] = dst[d].total_ms;
+      info->n_slots[d] = n_slots[d];
+      info->n_edges[d] = load[d];
+    }
+    info->zero_copy = (pos_pinned && p->n_edges && device_view_of_pinned(p->edges) != nullptr) ? 1 : 0;
   }
   return LFR_OK;
 }

@@ -1,14 +1,17 @@
-"""Multi-GPU: independent components partitioned across ranks.
+"""Multi-GPU, one PROCESS per GPU: independent components partitioned across ranks.
+
+(The single-process route — one call driving several devices, no collective at all — is
+lfr_solve_multi() in the C ABI, include/lfr.h; `solve --gpus N` uses that.  This module is the
+torchrun / torch.distributed variant for hosts that run one rank per GPU.)
 
 Every component is a self-contained problem (cross-component edges are dropped,
 solve.cc:123-125) and none exceeds #images nodes (solve.cc:586), so no component
-ever spans devices: ranks need no collective inside the LM loop.  One process
-per GPU (torch.distributed, NCCL over NVLink); each rank extracts the sub-graph
-of its components (the 80-byte edge records — the bulk — are partitioned, never
+ever spans devices: ranks need no collective inside the LM loop.  Each rank extracts the
+sub-graph of its components (the 80-byte edge records — the bulk — are partitioned, never
 replicated), solves it with lfr_solve on its own device, and the results are
-combined by one all-reduce(sum) of the position array (ranks write disjoint
-entries of a zero-initialised array, so the sum is exact and the result is
-bitwise identical to a 1-GPU solve) plus one all-reduce of the scalar totals.
+combined by ONE all-reduce(sum) of one packed buffer [positions | per-component stats | totals]
+(ranks write disjoint entries of a zero-initialised buffer, so the sum is exact and the result is
+bitwise identical to a 1-GPU solve).
 """
 from __future__ import annotations
 
@@ -95,30 +98,28 @@ def solve_sharded(p: Problem, rank: int, world: int, solve_fn: Callable, all_red
     parts = lpt_partition(slot_weights(p), world)
     sub, gnodes = shard_problem(p, parts[rank])
     pos_loc, st = solve_fn(sub)
-    pos = np.zeros((p.graph.n_nodes, 2), dtype=np.float64)
+    N, C = p.graph.n_nodes, p.n_components
+    # one packed buffer -> one collective: positions [2N] | iterations, termination, cost0, cost1 [C each] | 4 totals
+    buf = np.zeros(2 * N + 4 * C + 4, dtype=np.float64)
+    pos = buf[:2 * N].reshape(N, 2)
     pos[gnodes] = pos_loc
-    all_reduce_sum(pos)
-    C = p.n_components
-    iters = np.zeros(C, dtype=np.int64)
-    term = np.zeros(C, dtype=np.int64)
-    cost0 = np.zeros(C, dtype=np.float64)
-    cost1 = np.zeros(C, dtype=np.float64)
     mine = parts[rank]
-    iters[mine] = st["iterations"]
-    term[mine] = st["termination"]
-    cost0[mine] = st["initial_cost"]
-    cost1[mine] = st["final_cost"]
-    for a in (iters, term, cost0, cost1):
-        all_reduce_sum(a)
-    scal = np.array([float(st["total_iterations"]), float(st["total_line_search_steps"]),
-                     float(st["n_solved"]), float(st.get("n_kernel_launches", 0))], dtype=np.float64)
-    all_reduce_sum(scal)
-    out = dict(iterations=iters.astype(np.int32), termination=term.astype(np.int32), initial_cost=cost0,
-               final_cost=cost1, total_iterations=int(scal[0]), total_line_search_steps=int(scal[1]),
+    o = 2 * N
+    buf[o + mine] = st["iterations"]                  # small integers: exact in float64
+    buf[o + C + mine] = st["termination"]
+    buf[o + 2 * C + mine] = st["initial_cost"]
+    buf[o + 3 * C + mine] = st["final_cost"]
+    buf[o + 4 * C:] = [float(st["total_iterations"]), float(st["total_line_search_steps"]),
+                       float(st["n_solved"]), float(st.get("n_kernel_launches", 0))]
+    all_reduce_sum(buf)
+    scal = buf[o + 4 * C:]
+    out = dict(iterations=buf[o:o + C].astype(np.int32), termination=buf[o + C:o + 2 * C].astype(np.int32),
+               initial_cost=buf[o + 2 * C:o + 3 * C].copy(), final_cost=buf[o + 3 * C:o + 4 * C].copy(),
+               total_iterations=int(scal[0]), total_line_search_steps=int(scal[1]),
                n_solved=int(scal[2]), n_kernel_launches=int(scal[3]),
                kernel_ms=st.get("kernel_ms", 0.0), h2d_ms=st.get("h2d_ms", 0.0), d2h_ms=st.get("d2h_ms", 0.0),
                total_ms=st.get("total_ms", 0.0), shard_slots=[int(x.shape[0]) for x in parts])
-    return pos, out
+    return pos.copy(), out
 
 
 def solve_distributed(p: Problem, options=None):

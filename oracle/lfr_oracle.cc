@@ -1061,6 +1061,12 @@ int lfr_solve(const lfr_problem* p, const lfr_options* opt, double* positions,
   return LFR_OK;
 }
 
+int lfr_solve_multi(const lfr_problem* p, const lfr_options* opt, const int32_t*, int32_t, double* positions,
+                    lfr_stats* stats, lfr_multi_info* info) {
+  if (info) std::memset(info, 0, sizeof *info);
+  return lfr_solve(p, opt, positions, stats);  // the CPU pool has no devices to partition over
+}
+
 int lfr_plan_create(const lfr_problem*, const lfr_options*, const double*, lfr_plan**) {
   return fail(LFR_EUNSUPPORTED, "cpu-oracle has no device plans");
 }
