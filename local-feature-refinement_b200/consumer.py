@@ -63,3 +63,92 @@ def apply_solution(keypoints_by_image: Dict[str, np.ndarray], solution_bytes: by
         else:
             out[name] = apply_to_keypoints(kp, np.zeros(0, np.int64), np.zeros(0), np.zeros(0), 1.0)
     return out
+
+
+def import_features(colmap_path, method_name, database_path, image_path, match_list_path, matches_file, solution_file,
+                    run_colmap: bool = True):
+    """Drop-in for reconstruction-scripts/colmap_utils.py:77-223 `import_features`: clears the
+    feature tables of the COLMAP database, writes every image's (refined) keypoints as float32
+    [n, 4] blobs (colmap_utils.py:104-148) and the raw matches of every image pair as uint32 [m, 2]
+    blobs (colmap_utils.py:150-190: `.part.N` files, first occurrence of a pair id wins, columns
+    swapped when image_id1 > image_id2), then runs `colmap matches_importer` and returns the same
+    statistics dict.  The SolutionFile / MatchingFile are decoded by the native codec and applied
+    with array operations instead of one Python iteration per displacement / match."""
+    import os
+    import sqlite3
+    import subprocess
+
+    connection = sqlite3.connect(database_path)
+    cursor = connection.cursor()
+    cursor.execute("SELECT name FROM sqlite_master WHERE type='table' AND name='inlier_matches';")
+    inlier_matches_table_exists = cursor.fetchone() is not None
+    cursor.execute("DELETE FROM keypoints;")
+    cursor.execute("DELETE FROM descriptors;")
+    cursor.execute("DELETE FROM matches;")
+    cursor.execute("DELETE FROM inlier_matches;" if inlier_matches_table_exists else "DELETE FROM two_view_geometries;")
+    connection.commit()
+    images = {}
+    cursor.execute("SELECT name, image_id FROM images;")
+    for row in cursor:
+        images[row[0]] = row[1]
+    sol = None
+    if solution_file is not None:
+        with open(solution_file, "rb") as fh:
+            # a repeated image name: the reference keeps the LAST message of that name (dict overwrite, :112-114)
+            sol = {name: (fact, fi, di, dj) for name, fact, fi, di, dj in wire.decode_solution(fh.read())}
+    sum_num_features = 0
+    for image_name, image_id in images.items():
+        features = np.load(os.path.join(image_path, "%s.%s" % (image_name, method_name)), allow_pickle=True)
+        kp_in = features["keypoints"]
+        if sol is None:
+            kp = complete_keypoints(kp_in[:, :3] if kp_in.shape[0] else np.zeros([0, 4])).astype(np.float32)
+            kp[:, :2] += 0.5
+        elif image_name in sol:
+            fact, fi, di, dj = sol[image_name]
+            kp = apply_to_keypoints(kp_in, fi, di, dj, fact)
+        else:
+            kp = apply_to_keypoints(kp_in, np.zeros(0, np.int64), np.zeros(0), np.zeros(0), 1.0)
+        sum_num_features += kp.shape[0]
+        assert kp.shape[1] == 4
+        cursor.execute("INSERT INTO keypoints(image_id, rows, cols, data) VALUES(?, ?, ?, ?);",
+                       (image_id, kp.shape[0], kp.shape[1], kp.tobytes()))
+    connection.commit()
+
+    seen = set()
+    for path in wire.matches_files(matches_file):
+        with open(path, "rb") as fh:
+            ms = wire.decode_matching_file(fh.read())
+        for p in range(ms.n_pairs):
+            id1 = images[ms.image_names[int(ms.pair_img1[p])]]
+            id2 = images[ms.image_names[int(ms.pair_img2[p])]]
+            pair_id = 2147483647 * id2 + id1 if id1 > id2 else 2147483647 * id1 + id2     # colmap_utils.py:53-57
+            if pair_id in seen:
+                continue
+            seen.add(pair_id)
+            a, b = int(ms.pair_ptr[p]), int(ms.pair_ptr[p + 1])
+            if b > a:
+                cols = (ms.feat2[a:b], ms.feat1[a:b]) if id1 > id2 else (ms.feat1[a:b], ms.feat2[a:b])
+                matches = np.stack(cols, axis=1).astype(np.uint32)
+            else:
+                matches = np.zeros([0, 2])          # the reference's empty float64 array: an empty blob
+            cursor.execute("INSERT INTO matches(pair_id, rows, cols, data) VALUES(?, ?, ?, ?);",
+                           (pair_id, matches.shape[0], matches.shape[1], matches.tobytes()))
+        connection.commit()
+    cursor.close()
+    connection.close()
+
+    if run_colmap:
+        subprocess.call([os.path.join(colmap_path, "colmap"), "matches_importer", "--database_path", database_path,
+                         "--match_list_path", match_list_path, "--match_type", "pairs"])
+    connection = sqlite3.connect(database_path)
+    cursor = connection.cursor()
+    cursor.execute("SELECT count(*) FROM images;")
+    num_images = next(cursor)[0]
+    cursor.execute("SELECT count(*) FROM two_view_geometries WHERE rows > 0;")
+    num_inlier_pairs = next(cursor)[0]
+    cursor.execute("SELECT sum(rows) FROM two_view_geometries WHERE rows > 0;")
+    num_inlier_matches = next(cursor)[0]
+    cursor.close()
+    connection.close()
+    return dict(num_images=num_images, num_inlier_pairs=num_inlier_pairs, num_inlier_matches=num_inlier_matches,
+                avg_num_features=(sum_num_features / num_images))

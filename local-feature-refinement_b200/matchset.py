@@ -58,14 +58,16 @@ class MatchSet:
     # or instead of, the protobuf and skip serialise -> parse) --------------------
     def save_npz(self, path: str) -> None:
         """Write the flat arrays as one .npz (fp32 flows, exactly the wire content)."""
-        np.savez(path, image_names=np.array(self.image_names, dtype=object), pair_img1=self.pair_img1,
+        # names as a fixed-width unicode array: loadable with allow_pickle=False (an object array would
+        # make `solve --matches_file X.npz` unpickle whatever file it is handed)
+        np.savez(path, image_names=np.array(self.image_names, dtype=np.str_), pair_img1=self.pair_img1,
                  pair_img2=self.pair_img2, pair_fact1=self.pair_fact1, pair_fact2=self.pair_fact2,
                  pair_ptr=self.pair_ptr, feat1=self.feat1, feat2=self.feat2, sim=self.sim, disp1=self.disp1,
                  disp2=self.disp2)
 
     @staticmethod
     def load_npz(path: str) -> "MatchSet":
-        z = np.load(path, allow_pickle=True)
+        z = np.load(path, allow_pickle=False)
         ms = MatchSet(image_names=[str(x) for x in z["image_names"].tolist()],
                       pair_img1=z["pair_img1"].astype(np.int64), pair_img2=z["pair_img2"].astype(np.int64),
                       pair_fact1=z["pair_fact1"].astype(np.float32), pair_fact2=z["pair_fact2"].astype(np.float32),

@@ -25,6 +25,22 @@ def pytest_configure(config):
             mod.build()
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a CUDA device: skip them (instead of failing on cudaGetDeviceCount) when a
+    plain `pytest` runs on a CPU-only box.  `-m gpu` on the GPU box is unaffected."""
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (the solve has no CPU fallback)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle_util import load_oracle
