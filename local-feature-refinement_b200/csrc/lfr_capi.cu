@@ -159,6 +159,7 @@ struct lfr_plan {
   uint32_t n_large = 0;
   DevBuf L_comps, L_eidx, L_meta, L_inlist, L_twin, L_fdst, L_bmat, L_scr, L_q, L_node, L_outptr, L_inptr, L_freeof, L_x, L_xc, L_lof, L_vec;
   uint64_t L_total_free = 0;
+  uint32_t L_max_free = 0;
   uint32_t n_solved = 0;
   bool profile = false;
   // lfr_solve() zero-copy: staging tiers read the caller's pinned edge array / write the caller's
@@ -356,6 +357,7 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
 int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
   pl->n_large = (uint32_t)pl->large_slots.size();
   pl->L_total_free = 0;
+  pl->L_max_free = 0;
   if (pl->n_large == 0) return LFR_OK;
   std::vector<lfr::CtaComp> comps(pl->n_large);
   std::vector<uint32_t> eidx, meta, inlist, twin, node, outptr, inptr, lof;
@@ -437,6 +439,7 @@ int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
     cc.n_off = n_off;
     cc.f_off = f_off;
     cc.comp_index = k;
+    pl->L_max_free = std::max(pl->L_max_free, nf);
     e_off += ec;
     n_off += nc;
     f_off += nf;
@@ -566,6 +569,7 @@ int set_kernel_attrs() {
   int dev = 0;
   LFR_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 16 && done_for_device[dev]) return LFR_OK;
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -631,7 +635,10 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
     A.vec = pl->L_vec.as<double>();
     A.total_free = pl->L_total_free;
     if (hbm_edges_on_copy_stream) LFR_CUDA(cudaStreamWaitEvent(bs, pl->ev_edges, 0));
-    lfr::solve_cta_kernel<<<pl->n_large, lfr::kCtaThreads, 0, bs>>>(P_hbm, pl->K, A, pl->L_comps.as<lfr::CtaComp>());
+    // dynamic shared memory for the CG vectors of the largest component of this launch (13 doubles per free node)
+    const size_t cg_bytes = std::min<size_t>(200 * 1024, (size_t)pl->L_max_free * 13 * sizeof(double));
+    lfr::solve_cta_kernel<<<pl->n_large, lfr::kCtaThreads, cg_bytes, bs>>>(P_hbm, pl->K, A, pl->L_comps.as<lfr::CtaComp>(),
+                                                                          (unsigned)(cg_bytes / sizeof(double)));
     LFR_CUDA(cudaGetLastError());
   }
   for (int i = 0; i < nb; ++i) {

@@ -6,7 +6,7 @@
 // damped normal equations (S H S + D^2) y = S g are never formed: they are
 // solved matrix-free by conjugate gradients preconditioned with the inverse of
 // the 2x2 diagonal blocks (block-Jacobi), iterated to a relative residual of
-// 1e-13 so that the step is, to working precision, the exact solve Ceres'
+// 1e-14 and then refined on the true residual to 2e-15, so that the step is, to working precision, the exact solve Ceres'
 // SPARSE_NORMAL_CHOLESKY (solve.cc:147) returns:
 //
 //   q_e = a_e (x_d~ - M_e x_s~)             one thread per directed edge
@@ -308,10 +308,14 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
   }
   block_sum3(C, bb, rz, bad);
   bool ok = (bad == 0.0) && isfinite(bb);
-  const double tol2 = 1e-26 * bb;  // |r| <= 1e-13 |b|
+  const double tol2 = 1e-28 * bb;  // recurrence residual |r| <= 1e-14 |b| ...
   const int max_it = 8 * C.n + 100;
-  int it = 0;
-  if (ok && bb > 0.0) {
+  int it = 0, restarts = 0;
+  // ... then iterative refinement: the recurrence residual drifts away from b - A y by ~cond * eps,
+  // so CG is restarted from the TRUE residual until that is <= 2e-15 |b| (at most twice): the step is
+  // the exact solve of Ceres' SPARSE_NORMAL_CHOLESKY to working precision, which keeps the line
+  // search's discontinuous decisions on the oracle's side
+  while (ok && bb > 0.0) {
     for (; it < max_it; ++it) {
       double pw = 0.0, z1 = 0.0, z2 = 0.0;
       if (C.regular) {
@@ -350,6 +354,26 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
       for (int i = C.tid; i < C.n; i += kCtaThreads) C.p[i] = C.z[i] + beta * C.p[i];
       __syncthreads();
     }
+    if (!ok || it >= max_it || restarts >= 2) break;
+    // true residual r = S g - A y, z = M^-1 r, p = z
+    if (C.regular) cta_matvec_bcsr(C, C.y, C.w, C.pblk); else cta_matvec(C, C.y, C.w);
+    double rt = 0.0, rzt = 0.0, z3 = 0.0;
+    for (int f = C.tid; f < C.nf; f += kCtaThreads) {
+      const double r0 = C.S[2 * f] * C.g[2 * f] - C.w[2 * f], r1 = C.S[2 * f + 1] * C.g[2 * f + 1] - C.w[2 * f + 1];
+      const double z0 = C.pinv[3 * f] * r0 + C.pinv[3 * f + 1] * r1, z1 = C.pinv[3 * f + 1] * r0 + C.pinv[3 * f + 2] * r1;
+      C.r[2 * f] = r0;
+      C.r[2 * f + 1] = r1;
+      C.z[2 * f] = z0;
+      C.z[2 * f + 1] = z1;
+      C.p[2 * f] = z0;
+      C.p[2 * f + 1] = z1;
+      rt += r0 * r0 + r1 * r1;
+      rzt += r0 * z0 + r1 * z1;
+    }
+    block_sum3(C, rt, rzt, z3);
+    if (rt <= 4e-30 * bb || !(rzt > 0.0)) break;  // |b - A y| <= 2e-15 |b|
+    rz = rzt;
+    ++restarts;
   }
   *cg_iters += (unsigned)it;
   if (diag_mode && ok && bb > 0.0) {  // LFR_PROFILE: true residual |b - A y| / |b| of the returned solution
@@ -392,7 +416,7 @@ __device__ __forceinline__ void cta_candidate(const CtaCtx& C, double alpha, con
 }
 
 __global__ void __launch_bounds__(kCtaThreads)
-solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const CtaComp* comps) {
+solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const CtaComp* comps, unsigned smem_doubles) {
   __shared__ double red[3 * (kCtaThreads / 32)];
   const CtaComp cc = comps[blockIdx.x];
   CtaCtx C;
@@ -431,8 +455,25 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
   C.twin = A.twin + cc.e_off;
   C.fdst = A.fdst + cc.e_off;
   C.regular = cc.regular != 0;
-  __shared__ double psh[4096];  // the CG search direction is the randomly-gathered vector: keep it on chip
-  if (C.n <= 4096) C.p = psh;
+  // CG vectors on chip while they fit in the launch's dynamic shared memory, in order of how often an
+  // iteration touches them: p (randomly gathered by the matvec), w, r, z, y, then the preconditioner
+  extern __shared__ __align__(16) double cg_smem[];
+  {
+    size_t used = 0;
+    const size_t cap = smem_doubles;
+    auto take = [&](double*& ptr, size_t n_doubles) {
+      if (used + n_doubles <= cap) {
+        ptr = cg_smem + used;
+        used += n_doubles;
+      }
+    };
+    take(C.p, (size_t)C.n);
+    take(C.w, (size_t)C.n);
+    take(C.r, (size_t)C.n);
+    take(C.z, (size_t)C.n);
+    take(C.y, (size_t)C.n);
+    take(C.pinv, 3 * (size_t)C.nf);
+  }
   C.edges = P.edges;
   C.red = red;
   const uint32_t c = cc.slot;
