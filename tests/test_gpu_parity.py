@@ -375,30 +375,56 @@ def test_cta_pcg_tier_on_large_components(b200, oracle):
     assert np.array_equal(st_g["termination"], st_o["termination"])
 
 
-def test_cta_pcg_tier_up_to_400_unknowns(b200, oracle):
-    """Ring scene with components of up to ~200 nodes (~400 unknowns), solved by
-    PCG to a 1e-13 relative residual while the oracle factorises exactly.
+def _per_component_agreement(p, pos_g, st_g, pos_o, st_o):
+    err = np.zeros(p.n_components)
+    for c in range(p.n_components):
+        nodes = p.comp_nodes[p.comp_ptr[c]:p.comp_ptr[c + 1]].astype(int)
+        err[c] = np.abs(pos_g[nodes] - pos_o[nodes]).max() if nodes.size else 0.0
+    good = (err <= TOL_UNITS) & (st_g["iterations"] == st_o["iterations"]) & (st_g["termination"] == st_o["termination"])
+    return good, err
 
-    The two linear solves agree to ~1e-12, which keeps every LM decision the same
-    except where Ceres' line search is discontinuous in its input (two candidate
-    step sizes with near-equal interpolant values): such a component follows a
-    different, equally valid trajectory.  Bar: >= 99 % of the components within
-    1e-4 px with identical iteration counts, the rest within 1e-3 relative cost."""
+
+def test_cta_pcg_tier_up_to_400_unknowns(b200, oracle):
+    """Ring scene with components of up to ~200 nodes (~400 unknowns): block-Jacobi PCG, refined on
+    the true residual to 2e-15, against the oracle's exact factorisation.  EVERY component within
+    1e-4 px with identical iteration counts and termination reasons (round 1 needed a 99 % allowance
+    at a 1e-13 residual: a few line searches forked on ~1e-12 differences in the step)."""
     _, p = get_problem("ring200")
     sizes = np.diff(p.comp_ptr.astype(np.int64))
     assert sizes.max() > 150
     pos_g, st_g = b200.solve(p)
     pos_o, st_o = oracle.solve(p, oracle.default_options(n_threads=8))
-    err = np.zeros(p.n_components)
-    for c in range(p.n_components):
-        nodes = p.comp_nodes[p.comp_ptr[c]:p.comp_ptr[c + 1]].astype(int)
-        err[c] = np.abs(pos_g[nodes] - pos_o[nodes]).max()
-    good = (err <= TOL_UNITS) & (st_g["iterations"] == st_o["iterations"])
-    assert good.mean() >= 0.99, (good.mean(), err.max())
-    rest = ~good
-    rel = np.abs(st_g["final_cost"][rest] - st_o["final_cost"][rest]) / np.maximum(st_o["final_cost"][rest], 1e-12)
-    assert np.all(rel <= 1e-3), rel
-    assert np.all(err[rest] <= 5e-3)
+    good, err = _per_component_agreement(p, pos_g, st_g, pos_o, st_o)
+    assert good.all(), (int((~good).sum()), err.max())
+
+
+def test_madrid_topology_components_up_to_1000_nodes_match_oracle(b200, oracle):
+    """BASELINE.json configs[4] topology (1000 images on a ring + random partners, cfg5) at 5 % of the
+    keypoints: the size cap of solve.cc:586 is reached — components of up to 1000 nodes = 2000
+    unknowns, ~100 of them above 500 nodes.  The 24 largest components and every 6th of the others
+    are solved by the CTA tier and by the oracle (dense Cholesky: ~8 s per 1000-node component per
+    core, which is why this is a subset): every one within 1e-4 px, identical iteration counts.
+    (tools/gpu_cta_parity.py checks all 199 components: profiles/r02_cta_parity.json.)"""
+    import copy
+    import os
+    from lfr_b200 import build_problem, synth
+    p = build_problem(synth.generate("cfg5", scale=0.05))
+    sizes = np.diff(p.comp_ptr.astype(np.int64))
+    assert sizes.max() >= 990 and (sizes >= 500).sum() >= 50
+    slots = sorted(set(range(24)) | set(range(24, p.n_components, 6)))      # dispatch list is size-descending
+    q = copy.copy(p)
+    ptr, nodes = [0], []
+    for s_ in slots:
+        nodes.append(p.comp_nodes[p.comp_ptr[s_]:p.comp_ptr[s_ + 1]])
+        ptr.append(ptr[-1] + len(nodes[-1]))
+    q.comp_ptr = np.array(ptr, np.uint32)
+    q.comp_nodes = np.concatenate(nodes).astype(np.uint32)
+    q.comp_order = p.comp_order[slots]
+    pos_g, st_g = b200.solve(q)
+    pos_o, st_o = oracle.solve(q, oracle.default_options(n_threads=min(len(slots), os.cpu_count() or 8)))
+    good, err = _per_component_agreement(q, pos_g, st_g, pos_o, st_o)
+    assert good.all(), (int((~good).sum()), err.max())
+    assert st_g["total_iterations"] == st_o["total_iterations"] > 100
 
 
 def test_forced_pcg_matches_cholesky_path(b200, oracle):
@@ -507,11 +533,7 @@ def test_seed_fuzz(b200, oracle, seed):
             nodes = p.comp_nodes[p.comp_ptr[c]:p.comp_ptr[c + 1]].astype(int)
             err[c] = np.abs(pos_g[nodes] - pos_o[nodes]).max()
         good = (err <= TOL_UNITS) & (st_g["iterations"] == st_o["iterations"])
-        nfree = np.array([int((~p.is_root[p.comp_nodes[p.comp_ptr[c]:p.comp_ptr[c + 1]].astype(int)].astype(bool)).sum())
-                          for c in range(p.n_components)])
-        exact_tier = 2 * nfree <= 96           # register / Cholesky tiers: exact solves, must match everywhere
-        assert good[exact_tier].all(), (cfg, seed, err[exact_tier].max())
-        assert good.mean() >= 0.98, (cfg, seed)  # PCG tier: see test_cta_pcg_tier_up_to_400_unknowns
+        assert good.all(), (cfg, seed, err.max())      # every tier, every component
 
 
 @pytest.mark.parametrize("cfg,scale", [("cfg2", 0.3), ("cfg4", 0.25), ("ring60", 1.0)])
