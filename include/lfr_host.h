@@ -39,6 +39,11 @@ typedef struct lfr_host_input {
   const float* sim;
   const float* disp1;           /* [n_matches*18]                                 */
   const float* disp2;
+  /* optional: caller-owned destination of the 80-byte edge records (the bulk of the output; their
+   * number is known up front: 2 x the matches of the non-skipped pairs).  When given and large
+   * enough the stage writes them there directly and lfr_host_stage_export() skips its copy. */
+  lfr_edge* edges_out;
+  uint64_t edges_out_capacity;  /* in records                                     */
 } lfr_host_input;
 
 typedef struct lfr_host_sizes {

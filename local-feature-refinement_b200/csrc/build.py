@@ -41,7 +41,7 @@ def _stale(out, deps):
 
 def build_host(force: bool = False) -> str:
     if force or _stale(OUT_HOST, HOST_DEPS):
-        subprocess.check_call(["g++", "-std=c++17", "-O3", "-fPIC", "-shared", "-Wall", "-o", OUT_HOST] +
+        subprocess.check_call(["g++", "-std=c++17", "-O3", "-fPIC", "-shared", "-pthread", "-Wall", "-o", OUT_HOST] +
                               [os.path.join(HERE, s) for s in HOST_SOURCES])
     return OUT_HOST
 

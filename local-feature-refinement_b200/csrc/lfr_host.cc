@@ -6,8 +6,10 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <thread>
 #include <numeric>
 #include <unordered_map>
 #include <vector>
@@ -15,12 +17,39 @@
 #include "../../include/lfr_host.h"
 #include "lfr_cut.h"
 
+// the 80-byte edge records: the bulk of the stage's output (cfg5: 877 MB), so never value-initialised
+struct EdgeBuf {
+  lfr_edge* p = nullptr;
+  size_t n = 0;
+  bool owned = true;
+  ~EdgeBuf() {
+    if (owned) std::free(p);
+  }
+  bool alloc(size_t m) {
+    if (owned) std::free(p);
+    owned = true;
+    p = m ? static_cast<lfr_edge*>(std::malloc(m * sizeof(lfr_edge))) : nullptr;
+    n = m;
+    return m == 0 || p != nullptr;
+  }
+  void borrow(lfr_edge* q, size_t m) {  // caller-owned destination
+    if (owned) std::free(p);
+    owned = false;
+    p = q;
+    n = m;
+  }
+  lfr_edge& operator[](size_t i) { return p[i]; }
+  const lfr_edge& operator[](size_t i) const { return p[i]; }
+  const lfr_edge* data() const { return p; }
+  size_t size() const { return n; }
+};
+
 struct lfr_host_stage {
   uint32_t N = 0, T = 0, C = 0;
   uint64_t E = 0;
   std::vector<uint32_t> row_ptr, track, comp, comp_ptr, comp_nodes, comp_order, node_image, node_feat;
   std::vector<uint8_t> is_root;
-  std::vector<lfr_edge> edges;
+  EdgeBuf edges;
 };
 
 namespace {
@@ -214,8 +243,36 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   const uint64_t M = kept_matches.size();
   std::vector<uint32_t> n1(M), n2(M);
   {
-    FlatMap ids((size_t)(2 * M));
+    // (image, feature_idx) -> node id in order of first appearance.  Feature indices are keypoint
+    // numbers, so per image they are compact: a direct table per image (a few KB each, cache
+    // resident while a pair is processed) replaces the hash map whenever the tables stay small.
+    std::vector<uint32_t> max_feat(in->n_images, 0);
+    std::vector<uint8_t> img_used(in->n_images, 0);
+    for (uint64_t k = 0; k < M; ++k) {
+      const uint64_t m = kept_matches[k];
+      max_feat[m_img1[k]] = std::max(max_feat[m_img1[k]], in->feat1[m]);
+      max_feat[m_img2[k]] = std::max(max_feat[m_img2[k]], in->feat2[m]);
+      img_used[m_img1[k]] = img_used[m_img2[k]] = 1;
+    }
+    uint64_t table_size = 0;
+    std::vector<uint64_t> table_off(in->n_images, 0);
+    for (uint32_t i = 0; i < in->n_images; ++i) {
+      table_off[i] = table_size;
+      if (img_used[i]) table_size += (uint64_t)max_feat[i] + 1;
+    }
+    const bool dense = table_size <= 8 * (2 * M) + (1u << 20);
+    std::vector<uint32_t> table(dense ? table_size : 0, 0);   // node id + 1, 0 = not seen yet
+    FlatMap ids(dense ? 0 : (size_t)(2 * M));
     auto intern = [&](uint32_t img, uint32_t feat) {
+      if (dense) {
+        uint32_t& t = table[table_off[img] + feat];
+        if (t) return t - 1;
+        const uint32_t id = (uint32_t)hs->node_image.size();
+        t = id + 1;
+        hs->node_image.push_back(img);
+        hs->node_feat.push_back(feat);
+        return id;
+      }
       const uint64_t key = ((uint64_t)img << 32) | feat;
       bool fresh;
       const size_t slot = ids.find_or_insert(key, &fresh);
@@ -241,19 +298,42 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     ++hs->row_ptr[n2[k] + 1];
   }
   for (uint32_t v = 0; v < N; ++v) hs->row_ptr[v + 1] += hs->row_ptr[v];
-  hs->edges.resize(2 * M);
+  if (in->edges_out && in->edges_out_capacity >= 2 * M) {
+    hs->edges.borrow(in->edges_out, 2 * M);
+  } else if (!hs->edges.alloc(2 * M)) {
+    delete hs;
+    return LFR_ENOMEM;
+  }
   {
+    // out-edge slot of both directed edges of every match, in add_edge order (n1->n2 then n2->n1,
+    // solve.cc:477-478): sequential; the 80-byte record copies then run on several threads
     std::vector<uint32_t> fill(hs->row_ptr.begin(), hs->row_ptr.end() - (N ? 1 : 0));
-    for (uint64_t k = 0; k < M; ++k) {  // add_edge order: n1->n2 (disp2) then n2->n1 (disp1), solve.cc:477-478
-      const uint64_t m = kept_matches[k];
-      lfr_edge& e1 = hs->edges[fill[n1[k]]++];
-      std::memcpy(e1.flow, in->disp2 + 18 * m, 18 * sizeof(float));
-      e1.sim = in->sim[m];
-      e1.dst = n2[k];
-      lfr_edge& e2 = hs->edges[fill[n2[k]]++];
-      std::memcpy(e2.flow, in->disp1 + 18 * m, 18 * sizeof(float));
-      e2.sim = in->sim[m];
-      e2.dst = n1[k];
+    std::vector<uint32_t> slot1(M), slot2(M);
+    for (uint64_t k = 0; k < M; ++k) {
+      slot1[k] = fill[n1[k]]++;
+      slot2[k] = fill[n2[k]]++;
+    }
+    auto copy_range = [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t k = lo; k < hi; ++k) {
+        const uint64_t m = kept_matches[k];
+        lfr_edge& e1 = hs->edges[slot1[k]];
+        std::memcpy(e1.flow, in->disp2 + 18 * m, 18 * sizeof(float));   // n1 -> n2 carries disp2
+        e1.sim = in->sim[m];
+        e1.dst = n2[k];
+        lfr_edge& e2 = hs->edges[slot2[k]];
+        std::memcpy(e2.flow, in->disp1 + 18 * m, 18 * sizeof(float));   // n2 -> n1 carries disp1
+        e2.sim = in->sim[m];
+        e2.dst = n1[k];
+      }
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (M < (1u << 18)) ? 1u : std::min(8u, hw);
+    if (nt == 1) {
+      copy_range(0, M);
+    } else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; ++t) th.emplace_back(copy_range, M * t / nt, M * (t + 1) / nt);
+      for (auto& x : th) x.join();
     }
   }
   if (N == 0) {
@@ -279,11 +359,95 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   }
   const bool small_sets = in->n_images <= 64;  // image set of a union-find root as one 64-bit mask
   std::vector<uint64_t> mask(small_sets ? N : 0);
-  std::vector<std::vector<uint16_t>> imgs(small_sets ? 0 : N);
-  for (uint32_t v = 0; v < N; ++v) {
-    if (small_sets) mask[v] = 1ull << hs->node_image[v];
-    else imgs[v].assign(1, (uint16_t)hs->node_image[v]);
-  }
+  // more than 64 images: a root's image set is {its own image} while it is a singleton (no storage),
+  // a short sorted list up to kListMax entries, then a bitset of n_images bits from a pool
+  const uint32_t W = (in->n_images + 63) / 64;
+  constexpr uint32_t kListMax = 12;
+  std::vector<uint32_t> set_size(small_sets ? 0 : N, 1);
+  std::vector<int32_t> set_slot(small_sets ? 0 : N, -1);   // index into lists (size <= kListMax) or bitsets (above)
+  std::vector<uint16_t> lists;                               // kListMax entries per slot
+  std::vector<uint64_t> bitsets;                             // W words per slot
+  std::vector<int32_t> free_lists;
+  if (small_sets)
+    for (uint32_t v = 0; v < N; ++v) mask[v] = 1ull << hs->node_image[v];
+  auto set_has = [&](uint32_t r, uint16_t img) -> bool {
+    const uint32_t sz = set_size[r];
+    if (sz == 1) return (uint16_t)hs->node_image[r] == img;
+    if (sz <= kListMax) {
+      const uint16_t* l = &lists[(size_t)set_slot[r] * kListMax];
+      for (uint32_t i = 0; i < sz; ++i)
+        if (l[i] == img) return true;
+      return false;
+    }
+    return (bitsets[(size_t)set_slot[r] * W + (img >> 6)] >> (img & 63)) & 1ull;
+  };
+  // visit the images of root r
+  auto for_each_image = [&](uint32_t r, auto&& fn) {
+    const uint32_t sz = set_size[r];
+    if (sz == 1) {
+      fn((uint16_t)hs->node_image[r]);
+    } else if (sz <= kListMax) {
+      const uint16_t* l = &lists[(size_t)set_slot[r] * kListMax];
+      for (uint32_t i = 0; i < sz; ++i) fn(l[i]);
+    } else {
+      const uint64_t* b = &bitsets[(size_t)set_slot[r] * W];
+      for (uint32_t w = 0; w < W; ++w)
+        for (uint64_t m = b[w]; m; m &= m - 1) fn((uint16_t)(64 * w + __builtin_ctzll(m)));
+    }
+  };
+  auto sets_clash = [&](uint32_t a, uint32_t b) -> bool {  // a = the smaller set
+    if (set_size[a] > kListMax && set_size[b] > kListMax) {
+      const uint64_t* x = &bitsets[(size_t)set_slot[a] * W];
+      const uint64_t* y = &bitsets[(size_t)set_slot[b] * W];
+      for (uint32_t w = 0; w < W; ++w)
+        if (x[w] & y[w]) return true;
+      return false;
+    }
+    bool clash = false;
+    for_each_image(a, [&](uint16_t img) { clash = clash || set_has(b, img); });
+    return clash;
+  };
+  // dst <- dst U src (disjoint), src released
+  auto absorb = [&](uint32_t dst, uint32_t src) {
+    const uint32_t new_size = set_size[dst] + set_size[src];
+    if (new_size <= kListMax) {
+      if (set_slot[dst] < 0) {  // singleton -> list
+        int32_t sl;
+        if (!free_lists.empty()) {
+          sl = free_lists.back();
+          free_lists.pop_back();
+        } else {
+          sl = (int32_t)(lists.size() / kListMax);
+          lists.resize(lists.size() + kListMax);
+        }
+        lists[(size_t)sl * kListMax] = (uint16_t)hs->node_image[dst];
+        set_slot[dst] = sl;
+      }
+      uint16_t* l = &lists[(size_t)set_slot[dst] * kListMax];
+      uint32_t n = set_size[dst];
+      for_each_image(src, [&](uint16_t img) { l[n++] = img; });
+    } else {
+      if (set_size[dst] <= kListMax) {  // singleton / list -> bitset
+        const int32_t sl = (int32_t)(bitsets.size() / W);
+        bitsets.resize(bitsets.size() + W, 0);
+        uint64_t* b = &bitsets[(size_t)sl * W];
+        for_each_image(dst, [&](uint16_t img) { b[img >> 6] |= 1ull << (img & 63); });
+        if (set_slot[dst] >= 0) free_lists.push_back(set_slot[dst]);
+        set_slot[dst] = sl;
+      }
+      uint64_t* b = &bitsets[(size_t)set_slot[dst] * W];
+      if (set_size[src] > kListMax) {
+        const uint64_t* c = &bitsets[(size_t)set_slot[src] * W];
+        for (uint32_t w = 0; w < W; ++w) b[w] |= c[w];
+      } else {
+        for_each_image(src, [&](uint16_t img) { b[img >> 6] |= 1ull << (img & 63); });
+      }
+    }
+    if (set_slot[src] >= 0 && set_size[src] <= kListMax) free_lists.push_back(set_slot[src]);
+    set_size[dst] = new_size;
+    set_size[src] = 0;
+    set_slot[src] = -1;
+  };
   auto find = [&](uint32_t x) {
     uint32_t r = x;
     while (parent[r] != -1) r = (uint32_t)parent[r];
@@ -294,7 +458,6 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     }
     return r;
   };
-  std::vector<uint16_t> merged;
   for (uint64_t oi = M; oi-- > 0;) {
     const uint32_t k = order[oi];
     const uint32_t r1 = find(n1[k]), r2 = find(n2[k]);
@@ -312,23 +475,15 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
       }
       continue;
     }
-    const std::vector<uint16_t>&a = imgs[r1], &b = imgs[r2];
-    bool clash = false;  // std::set_intersection non-empty (solve.cc:507-511)
-    for (size_t i = 0, j = 0; i < a.size() && j < b.size();) {
-      if (a[i] == b[j]) { clash = true; break; }
-      if (a[i] < b[j]) ++i; else ++j;
-    }
-    if (clash) continue;
-    merged.resize(a.size() + b.size());
-    std::merge(a.begin(), a.end(), b.begin(), b.end(), merged.begin());
-    if (a.size() < b.size()) {  // solve.cc:513-521
+    // std::set_intersection non-empty (solve.cc:507-511); smaller set under larger, tie: root2 under root1 (:513-521)
+    const bool r1_smaller = set_size[r1] < set_size[r2];
+    if (sets_clash(r1_smaller ? r1 : r2, r1_smaller ? r2 : r1)) continue;
+    if (r1_smaller) {
       parent[r1] = (int32_t)r2;
-      imgs[r2] = merged;
-      std::vector<uint16_t>().swap(imgs[r1]);
+      absorb(r2, r1);
     } else {
       parent[r2] = (int32_t)r1;
-      imgs[r1] = merged;
-      std::vector<uint16_t>().swap(imgs[r2]);
+      absorb(r1, r2);
     }
   }
   hs->track.assign(N, 0);
@@ -341,7 +496,6 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   std::vector<uint32_t> nodes_in_track(T, 0);
   for (uint32_t v = 0; v < N; ++v) ++nodes_in_track[hs->track[v]];
   S.max_track_size = *std::max_element(nodes_in_track.begin(), nodes_in_track.end());
-  std::vector<std::vector<uint16_t>>().swap(imgs);
   // ---- H3: roots (solve.cc:552-582) -----------------------------------------------------------
   hs->is_root.assign(N, 0);
   {
@@ -482,7 +636,7 @@ int lfr_host_stage_export(const lfr_host_stage* hs, uint32_t* row_ptr, lfr_edge*
     if (dst && bytes) std::memcpy(dst, src, bytes);
   };
   cp(row_ptr, hs->row_ptr.data(), hs->row_ptr.size() * 4);
-  cp(edges, hs->edges.data(), hs->edges.size() * sizeof(lfr_edge));
+  if (edges != hs->edges.data()) cp(edges, hs->edges.data(), hs->edges.size() * sizeof(lfr_edge));
   cp(track, hs->track.data(), hs->track.size() * 4);
   cp(comp, hs->comp.data(), hs->comp.size() * 4);
   cp(is_root, hs->is_root.data(), hs->is_root.size());

@@ -398,7 +398,8 @@ def build_problem_native(ms: MatchSet, banned_images=(), log=None) -> Problem:
         _fields_ = [("n_pairs", C.c_uint64), ("n_matches", C.c_uint64), ("n_images", C.c_uint32),
                     ("pair_img1", C.c_void_p), ("pair_img2", C.c_void_p), ("pair_skip", C.c_void_p),
                     ("pair_ptr", C.c_void_p), ("feat1", C.c_void_p), ("feat2", C.c_void_p), ("sim", C.c_void_p),
-                    ("disp1", C.c_void_p), ("disp2", C.c_void_p)]
+                    ("disp1", C.c_void_p), ("disp2", C.c_void_p), ("edges_out", C.c_void_p),
+                    ("edges_out_capacity", C.c_uint64)]
 
     class HostSizes(C.Structure):
         _fields_ = [("n_nodes", C.c_uint32), ("n_tracks", C.c_uint32), ("n_components", C.c_uint32),
@@ -426,7 +427,12 @@ def build_problem_native(ms: MatchSet, banned_images=(), log=None) -> Problem:
         feat1=np.ascontiguousarray(ms.feat1, dtype=np.uint32), feat2=np.ascontiguousarray(ms.feat2, dtype=np.uint32),
         sim=np.ascontiguousarray(ms.sim, dtype=np.float32), disp1=np.ascontiguousarray(ms.disp1, dtype=np.float32),
         disp2=np.ascontiguousarray(ms.disp2, dtype=np.float32))
+    # the edge records (80 B each) are written straight into the array handed to lfr_solve
+    counts = (arrs["pair_ptr"][1:] - arrs["pair_ptr"][:-1]).astype(np.int64)
+    e_cap = 2 * int(counts[skip == 0].sum()) if ms.n_pairs else 0
+    edges = np.empty(e_cap, EDGE_DTYPE)
     inp = HostInput(n_pairs=ms.n_pairs, n_matches=ms.n_matches, n_images=len(ms.image_names),
+                    edges_out=(edges.ctypes.data if e_cap else None), edges_out_capacity=e_cap,
                     **{k: (v.ctypes.data if v.size else None) for k, v in arrs.items()})
     h = C.c_void_p()
     sz = HostSizes()
@@ -435,10 +441,15 @@ def build_problem_native(ms: MatchSet, banned_images=(), log=None) -> Problem:
         raise RuntimeError("lfr_host_stage_create failed (%d)" % rc)
     try:
         N, E, Cn = int(sz.n_nodes), int(sz.n_edges), int(sz.n_components)
-        row_ptr = np.zeros(N + 1, np.uint32); edges = np.zeros(E, EDGE_DTYPE)
-        track = np.zeros(N, np.uint32); comp = np.zeros(N, np.uint32); is_root = np.zeros(N, np.uint8)
-        comp_ptr = np.zeros(Cn + 1, np.uint32); comp_nodes = np.zeros(N, np.uint32); comp_order = np.zeros(Cn, np.uint32)
-        node_image = np.zeros(N, np.uint32); node_feat = np.zeros(N, np.uint32)
+        # np.empty: every array is overwritten by the export (the edge records alone are 80 B x E)
+        assert E == e_cap
+        row_ptr = np.empty(N + 1, np.uint32)
+        track = np.empty(N, np.uint32); comp = np.empty(N, np.uint32); is_root = np.empty(N, np.uint8)
+        comp_ptr = np.empty(Cn + 1, np.uint32); comp_nodes = np.empty(N, np.uint32); comp_order = np.empty(Cn, np.uint32)
+        node_image = np.empty(N, np.uint32); node_feat = np.empty(N, np.uint32)
+        if N == 0:
+            row_ptr[:] = 0
+            comp_ptr[:] = 0
         outs = [row_ptr, edges, track, comp, is_root, comp_ptr, comp_nodes, comp_order, node_image, node_feat]
         rc = L.lfr_host_stage_export(h, *[(a.ctypes.data if a.size else None) for a in outs])
         if rc != 0:

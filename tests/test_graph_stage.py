@@ -76,7 +76,7 @@ def test_partition_invariants(cfg, scale):
         assert p.comp_nodes[p.comp_ptr[slot]:p.comp_ptr[slot + 1]].tolist() == nodes_c
 
 
-@pytest.mark.parametrize("cfg,scale,seed", [("cfg1", 1.0, None), ("cfg2", 0.1, 4), ("cfg4", 0.1, 8), ("ring60", 0.5, 2),
+@pytest.mark.parametrize("cfg,scale,seed", [("cfg1", 1.0, None), ("cfg2", 0.1, 4), ("cfg4", 0.1, 8), ("ring60", 0.5, 2), ("ring200", 0.3, 5),
                                             ("cfg2", 1.0, None)])
 def test_native_host_stage_equals_numpy_stage(cfg, scale, seed):
     """csrc/lfr_host.cc (include/lfr_host.h) against graph.py, array for array."""
