@@ -123,6 +123,23 @@ def test_duplicate_pairs_take_the_serial_assembly_path(b200, oracle):
     assert np.array_equal(st_g["iterations"], st_o["iterations"])
 
 
+def test_dense_high_degree_small_component_does_not_fail_the_solve(b200, oracle):
+    """a small component whose nodes carry thousands of directed out-edges (here: the same
+    image pairs listed 45 times, as a densely matched dataset with many pair lists would) needs more
+    shared memory per component than one SM has in every staging tier; the schedule must move it to a
+    tier that keeps per-edge data in global memory (Cholesky warp kernel, then CTA tier) instead of
+    returning LFR_EUNSUPPORTED for the whole dataset."""
+    from lfr_b200 import MatchSet, build_problem, synth
+    ms = synth.generate("cfg2", scale=0.01, seed=33)
+    dense = MatchSet.concatenate([ms] + [ms.select_pairs(np.arange(ms.n_pairs))] * 44)
+    p = build_problem(dense)
+    deg = np.diff(p.graph.row_ptr.astype(np.int64))
+    per_comp = np.array([deg[p.comp_nodes[p.comp_ptr[c]:p.comp_ptr[c + 1]].astype(int)].sum()
+                         for c in range(p.n_components)])
+    assert per_comp.max() * 176 > 227 * 1024            # staged records + per-edge scratch (176 B / edge) exceed one SM's shared memory
+    _compare(b200, oracle, p)
+
+
 def _compare_dbg(b200, oracle, p, debug_flags, **opts):
     """_compare with lfr_options.debug_flags set on the GPU side only (the oracle ignores them)."""
     pos_g, st_g = b200.solve(p, b200.default_options(debug_flags=debug_flags, **opts))
