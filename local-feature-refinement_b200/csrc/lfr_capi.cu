@@ -172,6 +172,7 @@ struct lfr_plan {
   bool needs_hbm_edges = false;    // some bucket (smem-Cholesky warp tier, CTA tier) reads edges from global memory
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_edges = nullptr;  // bulk edge copy done (only the non-staging tiers wait for it)
+  cudaEvent_t ev_small = nullptr;  // fork / join of the second upload stream
   cudaStream_t streams[kMaxStreams] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxStreams] = {};
   int n_streams = 0;
@@ -219,6 +220,7 @@ void free_plan(lfr_plan* pl) {
   }
   if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
   if (pl->ev_edges) cudaEventDestroy(pl->ev_edges);
+  if (pl->ev_small) cudaEventDestroy(pl->ev_small);
   if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
   delete pl;
 }
@@ -501,12 +503,26 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
     LFR_TRY(upload(&pl->edges, p->edges, (size_t)p->n_edges, s));  // the bulk first: the DMA runs while the host schedules
     pl->edges_in_hbm = true;
   }
+  // the small per-node arrays gate the first launch: with zero-copy edges they ARE the upload, so they
+  // go out on two streams (two copy engines) instead of queueing behind each other
+  cudaStream_t s2 = s;
+  if (zc_edges) {
+    if (!pl->copy_stream) LFR_CUDA(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
+    if (!pl->ev_small) LFR_CUDA(cudaEventCreateWithFlags(&pl->ev_small, cudaEventDisableTiming));
+    s2 = pl->copy_stream;
+    LFR_CUDA(cudaEventRecord(pl->ev_small, s));          // orders s2's copies after whatever `s` ran before
+    LFR_CUDA(cudaStreamWaitEvent(s2, pl->ev_small, 0));
+  }
   LFR_TRY(upload(&pl->row_ptr, p->row_ptr, (size_t)p->n_nodes + 1, s));
-  LFR_TRY(upload(&pl->track, p->track, (size_t)p->n_nodes, s));
-  LFR_TRY(upload(&pl->comp, p->comp, (size_t)p->n_nodes, s));
-  LFR_TRY(upload(&pl->is_root, p->is_root, (size_t)p->n_nodes, s));
+  LFR_TRY(upload(&pl->track, p->track, (size_t)p->n_nodes, s2));
+  LFR_TRY(upload(&pl->comp, p->comp, (size_t)p->n_nodes, s2));
+  LFR_TRY(upload(&pl->is_root, p->is_root, (size_t)p->n_nodes, s2));
   LFR_TRY(upload(&pl->comp_ptr, p->comp_ptr, (size_t)p->n_components + 1, s));
   LFR_TRY(upload(&pl->comp_nodes, p->comp_nodes, (size_t)pl->total_slots, s));
+  if (s2 != s) {
+    LFR_CUDA(cudaEventRecord(pl->ev_small, s2));
+    LFR_CUDA(cudaStreamWaitEvent(s, pl->ev_small, 0));
+  }
   const size_t N = std::max<size_t>(pl->N, 1), C = std::max<size_t>(pl->C, 1);
   LFR_TRY(pl->local_of.reserve(sizeof(uint32_t) * N));
   LFR_TRY(pl->pos.reserve(sizeof(double) * 2 * N));

@@ -95,3 +95,12 @@ def test_invalid_problems_are_rejected(oracle):
     pos = np.zeros((p.graph.n_nodes, 2))
     assert oracle.lib.lfr_solve(C.byref(s), None, pos.ctypes.data, None) == -1
     assert b"row_ptr" in oracle.lib.lfr_last_error()
+
+
+def test_oracle_exports_solve_multi_with_single_device_semantics(oracle):
+    """lfr_solve_multi is part of include/lfr.h; the CPU oracle ignores `devices` and returns what lfr_solve does."""
+    from lfr_b200 import build_problem, synth
+    p = build_problem(synth.generate("cfg1", scale=0.3))
+    pos1, st1 = oracle.solve(p, oracle.default_options(n_threads=2))
+    pos2, st2 = oracle.solve_multi(p, [0, 1], oracle.default_options(n_threads=2))
+    assert np.array_equal(pos1, pos2) and np.array_equal(st1["iterations"], st2["iterations"])
