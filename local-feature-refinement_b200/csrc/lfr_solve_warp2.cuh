@@ -633,6 +633,8 @@ __device__ __forceinline__ void warp_setup(Ctx& C, uint32_t* rowstart, uint32_t*
   *nf_out = frun;
 }
 
+// (12 resident warps per SM = 168 registers for NREG <= 16; measured: 8 (255 registers, no spills)
+// and 16 (128 registers) change neither the single-scene latency nor the throughput, profiles/README.md)
 template <int WARPS, int NREG>
 __global__ void __launch_bounds__(WARPS * 32, (NREG > 16 ? 8 : 12) / WARPS)
 solve_warp2_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
