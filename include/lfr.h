@@ -190,6 +190,11 @@ typedef struct lfr_multi_info {
 int lfr_solve_multi(const lfr_problem* p, const lfr_options* o, const int32_t* devices, int32_t n_devices,
                     double* positions, lfr_stats* stats, lfr_multi_info* info);
 
+/* lfr_solve() / lfr_solve_multi() keep one grow-only workspace per device between calls (device
+ * buffers, pinned staging, streams) so that steady-state calls allocate nothing.  lfr_shutdown()
+ * releases them all; a later call simply re-creates what it needs.  No-op in the oracle. */
+void lfr_shutdown(void);
+
 /* ---- device-resident plan (b200 only; the oracle returns LFR_EUNSUPPORTED) --
  * lfr_plan_create copies the problem to HBM once; lfr_plan_solve re-runs the
  * whole solve from the stored initial positions, asynchronously on `stream`

@@ -763,10 +763,10 @@ int select_device(const lfr_options& o) {
   return LFR_OK;
 }
 
-// lfr_solve()'s workspace: per host thread and device, one cached plan (grow-only device
-// buffers), one non-blocking stream and the events that time the call — all created with that
-// device current.  Never freed: device memory is reclaimed at process exit, and calling into CUDA
-// from a thread-local destructor during teardown is not safe.
+// lfr_solve()'s workspace: per device (shared by all host threads, guarded by g_ws_mutex), one cached
+// plan (grow-only device buffers), one non-blocking stream and the events that time the call — all
+// created with that device current.  Kept until lfr_shutdown() or process exit (no destructor calls
+// into CUDA during teardown).
 struct DeviceWorkspace {
   lfr_plan* plan = nullptr;
   cudaStream_t stream = nullptr;
@@ -976,6 +976,23 @@ int lfr_solve(const lfr_problem* p, const lfr_options* opt, double* positions, l
   if (o.device < 0 || o.device >= kMaxDevices) return fail(LFR_EUNSUPPORTED, "device ordinal out of [0, 16)");
   std::lock_guard<std::mutex> lock(g_ws_mutex[o.device]);
   return solve_on_device(p, o, positions, st, nullptr, 0, nullptr);
+}
+
+void lfr_shutdown(void) {
+  // release the cached per-device workspaces of lfr_solve() / lfr_solve_multi() (device buffers,
+  // pinned staging, streams, events); the next call re-creates what it needs
+  for (int d = 0; d < kMaxDevices; ++d) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex[d]);
+    DeviceWorkspace& ws = g_ws[d];
+    if (!ws.ready) continue;
+    if (cudaSetDevice(d) == cudaSuccess) {
+      free_plan(ws.plan);
+      for (int i = 0; i < 4; ++i)
+        if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
+      if (ws.stream) cudaStreamDestroy(ws.stream);
+    }
+    ws = DeviceWorkspace();
+  }
 }
 
 int lfr_solve_multi(const lfr_problem* p, const lfr_options* opt, const int32_t* devices, int32_t n_devices,

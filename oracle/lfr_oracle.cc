@@ -1067,6 +1067,8 @@ int lfr_solve_multi(const lfr_problem* p, const lfr_options* opt, const int32_t*
   return lfr_solve(p, opt, positions, stats);  // the CPU pool has no devices to partition over
 }
 
+void lfr_shutdown(void) {}
+
 int lfr_plan_create(const lfr_problem*, const lfr_options*, const double*, lfr_plan**) {
   return fail(LFR_EUNSUPPORTED, "cpu-oracle has no device plans");
 }
