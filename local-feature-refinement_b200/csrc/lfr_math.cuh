@@ -164,28 +164,32 @@ __device__ __forceinline__ double newton_quotient(double f, double df) {
   return f * (double)__frcp_rn(__double2float_rn(df));
 }
 
+// One real root of q inside the bracket [a, b] (f(a), f(b) of opposite sign, q monotone there):
+// Newton's iteration started from the regula-falsi point of the bracket (the ends' values are
+// known, and the brackets are narrow: one grid cell or one monotone segment), kept inside the
+// shrinking bracket by a bisection step whenever Newton would leave it.  Stops after a step of
+// relative size <= 1e-8 (quadratic convergence: the error is then ~1e-16).  The oracle's fast
+// formulation runs the same operations.
 __device__ __forceinline__ double bracket_root(const double* q, int nq, double a, double b, double fa, double fb) {
   if (fa == 0.0) return a;
   if (fb == 0.0) return b;
-  double xl = fa < 0.0 ? a : b, xh = fa < 0.0 ? b : a;
-  double x = 0.5 * (a + b), dxold = fabs(b - a), dx = dxold, f, df;
-  horner2(q, nq, x, &f, &df);
+  double xl = fa < 0.0 ? a : b, xh = fa < 0.0 ? b : a;  // f(xl) < 0 < f(xh)
+  double x = a - fa * newton_quotient(b - a, fb - fa);
+  if (!(x > fmin(a, b) && x < fmax(a, b))) x = 0.5 * (a + b);
   for (int it = 0; it < 100; ++it) {
-    if ((((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
-      dxold = dx;
-      dx = 0.5 * (xh - xl);
-      x = xl + dx;
-      if (xl == x) return x;
-    } else {
-      dxold = dx;
-      dx = newton_quotient(f, df);
-      const double t = x;
-      x -= dx;
-      if (t == x) return x;
-    }
-    if (fabs(dx) <= 1e-8 * fabs(x)) return x;  // quadratic convergence: the error after this step is ~1e-16
+    double f, df;
     horner2(q, nq, x, &f, &df);
+    if (f == 0.0) return x;
     if (f < 0.0) xl = x; else xh = x;
+    double dx = newton_quotient(f, df);
+    double xn = x - dx;
+    if (!(xn > fmin(xl, xh) && xn < fmax(xl, xh))) {  // Newton leaves the bracket (or is not finite): bisect
+      xn = 0.5 * (xl + xh);
+      dx = x - xn;
+    }
+    if (xn == x) return x;
+    x = xn;
+    if (fabs(dx) <= 1e-8 * fabs(x)) return x;
   }
   return x;
 }
@@ -314,26 +318,24 @@ __device__ __forceinline__ double bracket_root_n(const double (&q)[N], double a,
   if (fa == 0.0) return a;
   if (fb == 0.0) return b;
   double xl = fa < 0.0 ? a : b, xh = fa < 0.0 ? b : a;
-  double x = 0.5 * (a + b), dxold = fabs(b - a), dx = dxold, f, df;
-  horner2_n<N>(q, x, &f, &df);
+  double x = a - fa * newton_quotient(b - a, fb - fa);
+  if (!(x > fmin(a, b) && x < fmax(a, b))) x = 0.5 * (a + b);
   LFR_PP_COUNT(9);
   for (int it = 0; it < 100; ++it) {
     LFR_PP_COUNT(8);
-    if ((((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
-      dxold = dx;
-      dx = 0.5 * (xh - xl);
-      x = xl + dx;
-      if (xl == x) return x;
-    } else {
-      dxold = dx;
-      dx = newton_quotient(f, df);
-      const double t = x;
-      x -= dx;
-      if (t == x) return x;
-    }
-    if (fabs(dx) <= 1e-8 * fabs(x)) return x;
+    double f, df;
     horner2_n<N>(q, x, &f, &df);
+    if (f == 0.0) return x;
     if (f < 0.0) xl = x; else xh = x;
+    double dx = newton_quotient(f, df);
+    double xn = x - dx;
+    if (!(xn > fmin(xl, xh) && xn < fmax(xl, xh))) {
+      xn = 0.5 * (xl + xh);
+      dx = x - xn;
+    }
+    if (xn == x) return x;
+    x = xn;
+    if (fabs(dx) <= 1e-8 * fabs(x)) return x;
   }
   return x;
 }

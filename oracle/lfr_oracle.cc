@@ -213,31 +213,31 @@ double newton_quotient(double f, double df) {
   return f * static_cast<double>(r);
 }
 
+// One real root of q inside the bracket [a, b] (opposite signs at the ends, q monotone there):
+// Newton from the regula-falsi point, bisection whenever a step would leave the shrinking bracket;
+// stops after a step of relative size <= 1e-8 (quadratic convergence: error ~1e-16 afterwards; the
+// 6e-8 relative error of newton_quotient only adds 6e-8 * 1e-8).  Same operations as
+// csrc/lfr_math.cuh::bracket_root.
 double bracket_root(const double* q, int nq, double a, double b, double fa, double fb) {
   if (fa == 0.0) return a;
   if (fb == 0.0) return b;
   double xl = fa < 0.0 ? a : b, xh = fa < 0.0 ? b : a;
-  double x = 0.5 * (a + b), dxold = std::fabs(b - a), dx = dxold, f, df;
-  horner2(q, nq, x, &f, &df);
+  double x = a - fa * newton_quotient(b - a, fb - fa);
+  if (!(x > std::fmin(a, b) && x < std::fmax(a, b))) x = 0.5 * (a + b);
   for (int it = 0; it < 100; ++it) {
-    if ((((x - xh) * df - f) * ((x - xl) * df - f) > 0.0) || (std::fabs(2.0 * f) > std::fabs(dxold * df))) {
-      dxold = dx;
-      dx = 0.5 * (xh - xl);
-      x = xl + dx;
-      if (xl == x) return x;
-    } else {
-      dxold = dx;
-      dx = newton_quotient(f, df);
-      const double t = x;
-      x -= dx;
-      if (t == x) return x;
-    }
-    // Newton converges quadratically: after a step of relative size <= 1e-8 the
-    // error is ~1e-16 (the 6e-8 relative error of newton_quotient only adds
-    // 6e-8 * 1e-8), so this is the last useful iteration
-    if (std::fabs(dx) <= 1e-8 * std::fabs(x)) return x;
+    double f, df;
     horner2(q, nq, x, &f, &df);
+    if (f == 0.0) return x;
     if (f < 0.0) xl = x; else xh = x;
+    double dx = newton_quotient(f, df);
+    double xn = x - dx;
+    if (!(xn > std::fmin(xl, xh) && xn < std::fmax(xl, xh))) {
+      xn = 0.5 * (xl + xh);
+      dx = x - xn;
+    }
+    if (xn == x) return x;
+    x = xn;
+    if (std::fabs(dx) <= 1e-8 * std::fabs(x)) return x;
   }
   return x;
 }
