@@ -183,7 +183,8 @@ __device__ __forceinline__ double bracket_root(const double* q, int nq, double a
     if (f < 0.0) xl = x; else xh = x;
     double dx = newton_quotient(f, df);
     double xn = x - dx;
-    if (!(xn > fmin(xl, xh) && xn < fmax(xl, xh))) {  // Newton leaves the bracket (or is not finite): bisect
+    if (xn == x) return x;  // converged to the last bit (checked before the bracket test: x itself is one end of the bracket)
+    if (!(xn >= fmin(xl, xh) && xn <= fmax(xl, xh))) {  // Newton leaves the bracket (or is not finite): bisect
       xn = 0.5 * (xl + xh);
       dx = x - xn;
     }
@@ -329,7 +330,8 @@ __device__ __forceinline__ double bracket_root_n(const double (&q)[N], double a,
     if (f < 0.0) xl = x; else xh = x;
     double dx = newton_quotient(f, df);
     double xn = x - dx;
-    if (!(xn > fmin(xl, xh) && xn < fmax(xl, xh))) {
+    if (xn == x) return x;  // converged to the last bit (checked before the bracket test: x itself is one end of the bracket)
+    if (!(xn >= fmin(xl, xh) && xn <= fmax(xl, xh))) {
       xn = 0.5 * (xl + xh);
       dx = x - xn;
     }

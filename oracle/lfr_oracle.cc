@@ -231,7 +231,8 @@ double bracket_root(const double* q, int nq, double a, double b, double fa, doub
     if (f < 0.0) xl = x; else xh = x;
     double dx = newton_quotient(f, df);
     double xn = x - dx;
-    if (!(xn > std::fmin(xl, xh) && xn < std::fmax(xl, xh))) {
+    if (xn == x) return x;  // converged to the last bit (checked before the bracket test: x itself is one end of the bracket)
+    if (!(xn >= std::fmin(xl, xh) && xn <= std::fmax(xl, xh))) {
       xn = 0.5 * (xl + xh);
       dx = x - xn;
     }
