@@ -3,6 +3,7 @@
 // launches, and result download.  No CPU fallback: every entry point that
 // computes fails with LFR_ENODEV / LFR_ECUDA when no device is usable.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +18,14 @@
 namespace {
 
 thread_local std::string g_last_error;
+
+// host-side timeline of the calling thread's last lfr_solve(): microseconds since the call began at
+// {small uploads queued, schedule built, plan filled, kernels queued, stats back, return}
+thread_local double g_host_marks[8] = {};
+thread_local std::chrono::steady_clock::time_point g_host_t0;
+inline void host_mark(int i) {
+  g_host_marks[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - g_host_t0).count();
+}
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -107,6 +116,13 @@ struct DevBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
+// One launch of the CTA tier: a size class of large components (its dynamic shared memory and the
+// register cap MINB decide how many of them an SM runs at once).
+struct CtaGroup {
+  uint32_t first = 0, n = 0, max_free = 0;
+  int minb = 2;
+};
+
 struct Bucket {
   uint32_t offset = 0;  // into the bucket-list buffer
   uint32_t n = 0;
@@ -138,7 +154,7 @@ struct lfr_plan {
   uint64_t E = 0;
   uint32_t total_slots = 0;
   DevBuf row_ptr, edges, track, comp, is_root, comp_ptr, comp_nodes, local_of, pos, pos_init, stats, cycles, times, lists;
-  // `stats` is one block (one memset, one D2H copy): cost0[Cp] cost1[Cp] iter[Cp] term[Cp] ls[Cp] kept[Cp] err[2]
+  // `stats` is one block (one memset, one D2H copy): cost0[Cp] cost1[Cp] iter[Cp] term[Cp] ls[Cp] kept[Cp] err[2] pull[2 x u64]
   uint32_t Cp = 0;               // C rounded up to an even count
   bool pos_is_staged = false;    // lfr_solve(): the start point was uploaded straight into `pos`
   void* h_stage = nullptr;       // pinned host staging for the stats block
@@ -150,14 +166,23 @@ struct lfr_plan {
   uint32_t* d_ls() const { return reinterpret_cast<uint32_t*>(d_term() + Cp); }
   uint32_t* d_kept() const { return d_ls() + Cp; }
   int* d_err() const { return reinterpret_cast<int*>(d_kept() + Cp); }
-  size_t stats_bytes() const { return 16 * (size_t)Cp + 16 * (size_t)Cp + 8; }
+  unsigned long long* d_pull() const { return reinterpret_cast<unsigned long long*>(d_err() + 2); }  // {ticketed, arrived} bytes
+  size_t stats_bytes() const { return 16 * (size_t)Cp + 16 * (size_t)Cp + 8 + 16; }
   std::vector<Bucket> buckets;
   std::vector<uint32_t> comp_size;  // nodes per dispatch slot
   std::vector<uint32_t> list_host;
   // CTA tier (block-Jacobi PCG): components with more than kMaxWarpN2 unknowns, or all with linear_solver = 2
+  struct SchedDim { int e, nc, n2; };
+  std::vector<uint16_t> sched_key;        // build_buckets scratch: (variant, shared-memory class) of every slot
+  std::vector<SchedDim> sched_dim;
   std::vector<uint32_t> large_slots;
+  std::vector<uint64_t> large_cand;       // candidate out-edges of each large component (row_ptr sums)
+  std::vector<uint32_t> large_free;       // its non-root nodes (upper bound of the free nodes)
+  std::vector<uint64_t> large_ell;        // its sliced-ELL slots (32 x the largest candidate out-degree of every 32-node slice)
+  std::vector<lfr::CtaComp> L_comps_host;
+  std::vector<CtaGroup> cta_groups;
   uint32_t n_large = 0;
-  DevBuf L_comps, L_eidx, L_meta, L_inlist, L_twin, L_fdst, L_bmat, L_scr, L_q, L_node, L_outptr, L_inptr, L_freeof, L_x, L_xc, L_lof, L_vec;
+  DevBuf L_comps, L_rec, L_meta, L_inlist, L_twin, L_fdst, L_bE01, L_bE23, L_fdstE, L_ell_base, L_scr, L_q, L_node, L_outptr, L_inptr, L_freeof, L_x, L_xc, L_lof, L_vec;
   uint64_t L_total_free = 0;
   uint32_t L_max_free = 0;
   uint32_t n_solved = 0;
@@ -169,13 +194,38 @@ struct lfr_plan {
   const uint8_t* slot_owner = nullptr;  // lfr_solve_multi(): owner[c] of every dispatch slot, this plan solves owner == owner_id
   uint8_t owner_id = 0;
   bool edges_in_hbm = false;       // the edge array was (or is being) copied to `edges`
-  bool needs_hbm_edges = false;    // some bucket (smem-Cholesky warp tier, CTA tier) reads edges from global memory
+  bool needs_hbm_edges = false;    // some bucket (smem-Cholesky warp tier) reads edge records from global memory by index
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_edges = nullptr;  // bulk edge copy done (only the non-staging tiers wait for it)
   cudaEvent_t ev_small = nullptr;  // fork / join of the second upload stream
   cudaStream_t streams[kMaxStreams] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxStreams] = {};
   int n_streams = 0;
+
+  lfr::CtaArrays cta_arrays() const {
+    lfr::CtaArrays A;
+    A.rec = L_rec.as<float4>();
+    A.meta = L_meta.as<uint32_t>();
+    A.inlist = L_inlist.as<uint32_t>();
+    A.twin = L_twin.as<uint32_t>();
+    A.fdst = L_fdst.as<int32_t>();
+    A.bE01 = L_bE01.as<double2>();
+    A.bE23 = L_bE23.as<double2>();
+    A.fdstE = L_fdstE.as<int32_t>();
+    A.ell_base = L_ell_base.as<uint32_t>();
+    A.scr = L_scr.as<double>();
+    A.q = L_q.as<double>();
+    A.node = L_node.as<uint32_t>();
+    A.outptr = L_outptr.as<uint32_t>();
+    A.inptr = L_inptr.as<uint32_t>();
+    A.freeof = L_freeof.as<int32_t>();
+    A.x = L_x.as<double>();
+    A.xc = L_xc.as<double>();
+    A.lof = L_lof.as<uint32_t>();
+    A.vec = L_vec.as<double>();
+    A.total_free = L_total_free;
+    return A;
+  }
 
   lfr::DevProblem dev() const {
     lfr::DevProblem P;
@@ -191,6 +241,8 @@ struct lfr_plan {
     P.positions = pos.as<double>();
     P.positions_out = zc_positions ? zc_positions : pos.as<double>();
     P.stage_mode = (opt.debug_flags & LFR_DBG_STAGE_LDG) ? 0 : 1;
+    P.pull_ctr = d_pull();
+    P.pull_window = 0;  // set by launch_solve for zero-copy staging only
     P.st_iter = d_iter();
     P.st_term = d_term();
     P.st_cost0 = d_cost0();
@@ -209,8 +261,8 @@ namespace {
 void free_plan(lfr_plan* pl) {
   if (!pl) return;
   DevBuf* bufs[] = {&pl->row_ptr, &pl->edges, &pl->track, &pl->comp, &pl->is_root, &pl->comp_ptr, &pl->comp_nodes,
-                    &pl->local_of, &pl->pos, &pl->pos_init, &pl->stats, &pl->cycles, &pl->times, &pl->lists, &pl->L_comps, &pl->L_eidx, &pl->L_meta,
-                    &pl->L_inlist, &pl->L_twin, &pl->L_fdst, &pl->L_bmat, &pl->L_scr, &pl->L_q, &pl->L_node, &pl->L_outptr, &pl->L_inptr, &pl->L_freeof,
+                    &pl->local_of, &pl->pos, &pl->pos_init, &pl->stats, &pl->cycles, &pl->times, &pl->lists, &pl->L_comps, &pl->L_rec, &pl->L_meta,
+                    &pl->L_inlist, &pl->L_twin, &pl->L_fdst, &pl->L_bE01, &pl->L_bE23, &pl->L_fdstE, &pl->L_ell_base, &pl->L_scr, &pl->L_q, &pl->L_node, &pl->L_outptr, &pl->L_inptr, &pl->L_freeof,
                     &pl->L_x, &pl->L_xc, &pl->L_lof, &pl->L_vec};
   for (DevBuf* b : bufs) b->release();
   if (pl->h_stage) cudaFreeHost(pl->h_stage);
@@ -238,11 +290,12 @@ int upload(DevBuf* d, const T* h, size_t count, cudaStream_t s) {
 // launched on concurrent streams, largest components first.
 int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   static const int kClass[] = {2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 57344, kMaxSmemPerBlock};
-  const int n_class = sizeof(kClass) / sizeof(kClass[0]);
+  constexpr int n_class = sizeof(kClass) / sizeof(kClass[0]);
   // register warp kernel (8..32), register tile kernel (132 = 64 threads x NREG 32; 48, 64: 64 threads;
   // 80: 128 threads), smem-Cholesky warp kernel (0)
   static const int kVariant[9] = {8, 16, 24, 32, 132, 48, 64, 80, 0};
-  const int kNV = 9, kV1 = 8;
+  constexpr int kNV = 9, kV1 = 8, kKeys = kNV * n_class;
+  constexpr uint16_t kNoKey = 0xffff;
   auto is_tile = [](int vi) { return vi >= 4 && vi <= 7; };
   const int dbg = pl->opt.debug_flags;
   const bool no_tile = (dbg & LFR_DBG_NO_TILE) != 0;
@@ -250,42 +303,68 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   // instead of the one-warp kernel (their edge evaluation is split over 64 threads)
   const int tf = (dbg >> LFR_DBG_TILE_FROM_SHIFT) & 0xff;
   const int tile_from = no_tile ? 32 : (tf ? tf : kTileFromDefault);
-  std::vector<std::vector<uint32_t>> members(kNV * n_class);
-  std::vector<Bucket> caps(kNV * n_class);
-  pl->comp_size.resize(p->n_components);
-  pl->n_solved = 0;
-  pl->buckets.clear();
-  pl->list_host.clear();
   const bool force_v1 = (dbg & LFR_DBG_FORCE_SMEM_CHOLESKY) != 0;
   const bool force_pcg = pl->opt.linear_solver == 2;
-  pl->large_slots.clear();
   auto layout_bytes = [&](int vi, int e, int nc, int n2) {
     return (vi == kV1) ? lfr::WarpLayout(e, nc, n2).total
                        : (is_tile(vi) ? lfr::TileLayout(e, nc, n2).total : lfr::Warp2Layout(e, nc, n2).total);
   };
-  struct Dim { int e, nc, n2; };
-  std::vector<Dim> dim(p->n_components, Dim{0, 0, 0});
-  for (uint32_t c = 0; c < p->n_components; ++c) {
-    const uint32_t beg = p->comp_ptr[c], end = p->comp_ptr[c + 1];
+  // This runs on the calling thread while the GPU waits for its first launch: one pass over the
+  // components into flat, reused arrays (no per-call allocation once the plan is warm), then a
+  // counting sort of the slots by (variant, shared-memory class).
+  const uint32_t C = p->n_components;
+  pl->comp_size.resize(C);
+  pl->sched_key.resize(C);
+  pl->sched_dim.resize(C);
+  pl->n_solved = 0;
+  pl->buckets.clear();
+  pl->large_slots.clear();
+  pl->large_cand.clear();
+  pl->large_free.clear();
+  pl->large_ell.clear();
+  Bucket caps[kKeys];
+  uint32_t count[kKeys] = {};
+  const uint32_t* comp_ptr = p->comp_ptr;
+  const uint32_t* comp_nodes = p->comp_nodes;
+  const uint32_t* row_ptr = p->row_ptr;
+  const uint8_t* is_root = p->is_root;
+  const uint8_t* owner = pl->slot_owner;
+  const uint32_t n_nodes = p->n_nodes;
+  uint16_t* key_of = pl->sched_key.data();
+  lfr_plan::SchedDim* dim = pl->sched_dim.data();
+  for (uint32_t c = 0; c < C; ++c) {
+    const uint32_t beg = comp_ptr[c], end = comp_ptr[c + 1];
     if (end < beg || end > pl->total_slots) return fail(LFR_EINVAL, "comp_ptr not monotone");
     const uint32_t nc = end - beg;
     pl->comp_size[c] = nc;
+    key_of[c] = kNoKey;
     if (nc <= 1) continue;  // solve.cc:619-622
-    if (pl->slot_owner && pl->slot_owner[c] != pl->owner_id) continue;  // another device's component
+    if (owner && owner[c] != pl->owner_id) continue;  // another device's component
     ++pl->n_solved;
     uint64_t eup = 0;
     uint32_t nfree = 0;
     for (uint32_t i = beg; i < end; ++i) {
-      const uint32_t v = p->comp_nodes[i];
-      if (v >= p->n_nodes) return fail(LFR_EINVAL, "comp_nodes out of range");
-      if (p->row_ptr[v + 1] < p->row_ptr[v]) return fail(LFR_EINVAL, "row_ptr not monotone");
-      eup += p->row_ptr[v + 1] - p->row_ptr[v];
-      nfree += p->is_root[v] ? 0 : 1;
+      const uint32_t v = comp_nodes[i];
+      if (v >= n_nodes) return fail(LFR_EINVAL, "comp_nodes out of range");
+      const uint32_t r0 = row_ptr[v], r1 = row_ptr[v + 1];
+      if (r1 < r0) return fail(LFR_EINVAL, "row_ptr not monotone");
+      eup += r1 - r0;
+      nfree += is_root[v] ? 0 : 1;
     }
     const int n2 = std::max(2 * (int)nfree, 2);
     auto to_cta_tier = [&]() -> int {
       if (nc > 16383) return fail(LFR_EUNSUPPORTED, "component with more than 16383 nodes");
       pl->large_slots.push_back(c);
+      pl->large_cand.push_back(eup);
+      pl->large_free.push_back(nfree);
+      uint64_t slots = 0;
+      for (uint32_t i0 = beg; i0 < end; i0 += 32) {
+        uint32_t wmax = 0;
+        for (uint32_t i = i0; i < std::min(end, i0 + 32); ++i) wmax = std::max(wmax, row_ptr[comp_nodes[i] + 1] - row_ptr[comp_nodes[i]]);
+        slots += 32ull * wmax;
+      }
+      if (slots > 0xffffffffull) return fail(LFR_EUNSUPPORTED, "component too dense for the CTA tier's block layout");
+      pl->large_ell.push_back(slots);
       return LFR_OK;
     };
     if (force_pcg || n2 > lfr::kMaxWarpN2 || nc > (uint32_t)lfr::kMaxWarpNodes || eup > 65535) {
@@ -309,43 +388,60 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       continue;
     }
     int k = 0;
-    while (k < n_class && need > kClass[k]) ++k;
-    Bucket& cb = caps[vi * n_class + k];
-    members[vi * n_class + k].push_back(c);
-    dim[c] = Dim{e, (int)nc, n2};
+    while (need > kClass[k]) ++k;  // need <= kClass[n_class - 1] here
+    const int key = vi * n_class + k;
+    key_of[c] = (uint16_t)key;
+    dim[c] = lfr_plan::SchedDim{e, (int)nc, n2};
+    Bucket& cb = caps[key];
+    ++count[key];
     cb.emax = std::max(cb.emax, e);
     cb.ncmax = std::max(cb.ncmax, (int)nc);
     cb.n2max = std::max(cb.n2max, n2);
   }
-  pl->needs_hbm_edges = !pl->large_slots.empty();
-  auto emit = [&](int vi, const Bucket& cap, const uint32_t* mem, size_t n_mem) {
+  // emission order: largest shared-memory class first, within a class the higher tiers first
+  uint32_t start[kKeys], total = 0;
+  for (int k = n_class - 1; k >= 0; --k)
+    for (int vi = kNV - 1; vi >= 0; --vi) {
+      start[vi * n_class + k] = total;
+      total += count[vi * n_class + k];
+    }
+  pl->list_host.resize(total);
+  {
+    uint32_t fill[kKeys];
+    std::memcpy(fill, start, sizeof(fill));
+    uint32_t* list = pl->list_host.data();
+    for (uint32_t c = 0; c < C; ++c)
+      if (key_of[c] != kNoKey) list[fill[key_of[c]]++] = c;  // ascending slot index inside a bucket
+  }
+  pl->needs_hbm_edges = false;
+  auto emit = [&](int vi, const Bucket& cap, uint32_t offset, uint32_t n_mem) {
     Bucket b = cap;
     b.variant = kVariant[vi];
-    b.n = (uint32_t)n_mem;
-    b.offset = (uint32_t)pl->list_host.size();
+    b.n = n_mem;
+    b.offset = offset;
     b.smem_per_warp = layout_bytes(vi, b.emax, b.ncmax, b.n2max);
     b.warps = (4 * b.smem_per_warp <= kMaxSmemPerBlock) ? 4 : 1;
     if (b.variant >= 48) b.warps = 1;  // tile kernels: one component per CTA
     if (b.warps == 1 && b.variant != 0 && b.variant < 48) b.variant = 32;  // only <1,32> is instantiated for single-warp CTAs
-    pl->list_host.insert(pl->list_host.end(), mem, mem + n_mem);
     pl->buckets.push_back(b);
-    if (!b.stages_edges()) pl->needs_hbm_edges = true;
+    if (!b.stages_edges()) pl->needs_hbm_edges = true;  // the Cholesky warp tier reads records from HBM by global index
   };
-  for (int k = n_class - 1; k >= 0; --k) {  // largest first
+  for (int k = n_class - 1; k >= 0; --k) {
     for (int vi = kNV - 1; vi >= 0; --vi) {
-      const std::vector<uint32_t>& mem = members[vi * n_class + k];
-      if (mem.empty()) continue;
-      const Bucket& cap = caps[vi * n_class + k];
+      const int key = vi * n_class + k;
+      if (!count[key]) continue;
+      const Bucket& cap = caps[key];
       if (layout_bytes(vi, cap.emax, cap.ncmax, cap.n2max) <= kMaxSmemPerBlock) {
-        emit(vi, cap, mem.data(), mem.size());
+        emit(vi, cap, start[key], count[key]);
       } else {
         // every member fits on its own but the union of their maxima does not: one launch each
-        for (uint32_t c : mem) {
+        for (uint32_t i = 0; i < count[key]; ++i) {
+          const uint32_t c = pl->list_host[start[key] + i];
           Bucket one;
           one.emax = dim[c].e;
           one.ncmax = dim[c].nc;
           one.n2max = dim[c].n2;
-          emit(vi, one, &c, 1);
+          emit(vi, one, start[key] + i, 1);
         }
       }
     }
@@ -353,119 +449,87 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   return LFR_OK;
 }
 
-// Host-side preparation of the CTA-tier components (solve.cc:98-143 for each):
-// kept-edge lists with local indices and loss kinds, in-edge lists, free-variable
-// numbering.  These are the few components too large for one warp.
+// CTA-tier components: the host only lays out per-component offsets (upper bounds: candidate edges
+// from row_ptr, non-root nodes) and sizes the HBM arrays; the kept-edge / in-edge lists, free-variable
+// numbering and twins are built on the device by cta_prepare_kernel (launched by fill_plan once the
+// edge records and local_of are in HBM).
 int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
   pl->n_large = (uint32_t)pl->large_slots.size();
   pl->L_total_free = 0;
   pl->L_max_free = 0;
+  pl->cta_groups.clear();
   if (pl->n_large == 0) return LFR_OK;
-  std::vector<lfr::CtaComp> comps(pl->n_large);
-  std::vector<uint32_t> eidx, meta, inlist, twin, node, outptr, inptr, lof;
-  std::vector<int32_t> freeof, fdst;
-  std::vector<int32_t> local(p->n_nodes, -1);
-  uint64_t e_off = 0, n_off = 0, f_off = 0;
-  for (uint32_t k = 0; k < pl->n_large; ++k) {
-    const uint32_t c = pl->large_slots[k];
-    const uint32_t beg = p->comp_ptr[c], nc = p->comp_ptr[c + 1] - beg;
-    for (uint32_t l = 0; l < nc; ++l) local[p->comp_nodes[beg + l]] = (int32_t)l;
-    const size_t e0 = eidx.size();
-    std::vector<uint32_t> cin(nc, 0), cout(nc, 0);
-    outptr.push_back(0);
-    for (uint32_t l = 0; l < nc; ++l) {
-      const uint32_t v = p->comp_nodes[beg + l];
-      node.push_back(v);
-      for (uint32_t e = p->row_ptr[v]; e < p->row_ptr[v + 1]; ++e) {
-        const uint32_t dst = p->edges[e].dst;
-        if (dst >= p->n_nodes || dst == v) return fail(LFR_EINVAL, "edge with dst out of range or a self edge");
-        uint32_t kind;
-        if (p->track[v] == p->track[dst]) kind = LFR_EDGE_CAUCHY;        // solve.cc:105
-        else if (p->comp[v] == p->comp[dst]) kind = LFR_EDGE_TUKEY;      // solve.cc:114
-        else continue;                                                   // solve.cc:123
-        if (p->is_root[v] && p->is_root[dst]) continue;                  // all-constant block (A.1)
-        const int32_t dl = local[dst];
-        if (dl < 0) return fail(LFR_EINVAL, "component_idx and nodes_in_component disagree");
-        eidx.push_back(e);
-        meta.push_back(l | ((uint32_t)dl << 14) | (kind << 28));
-        ++cout[l];
-        ++cin[dl];
-      }
-      outptr.push_back((uint32_t)(eidx.size() - e0));
+  std::vector<lfr::CtaComp>& comps = pl->L_comps_host;  // plan member: the async upload reads it
+  comps.assign(pl->n_large, lfr::CtaComp{});
+  // size classes by free nodes (upper bound): 104 bytes of CG vectors per free node in shared memory
+  // -> 1 / 2 / 4 / 8 components per SM by shared memory; registers cap it at MINB
+  static const uint32_t kClassMaxFree[4] = {0xffffffffu, 1008, 504, 250};
+  int minb[4] = {2, 2, 3, 4};
+  if (const char* e = std::getenv("LFR_CTA_MINB")) {  // tuning hook: "2,2,3,4"
+    int a[4];
+    if (std::sscanf(e, "%d,%d,%d,%d", &a[0], &a[1], &a[2], &a[3]) == 4)
+      for (int i = 0; i < 4; ++i) minb[i] = std::min(4, std::max(2, a[i]));
+  }
+  auto class_of = [&](uint32_t nfree) { return nfree > kClassMaxFree[1] ? 0 : (nfree > kClassMaxFree[2] ? 1 : (nfree > kClassMaxFree[3] ? 2 : 3)); };
+  pl->cta_groups.clear();
+  uint64_t e_off = 0, n_off = 0, f_off = 0, ell_off = 0, s_off = 0;
+  uint32_t k = 0;
+  for (int cls = 0; cls < 4; ++cls) {
+    CtaGroup g;
+    g.first = k;
+    g.minb = minb[cls];
+    for (uint32_t i = 0; i < pl->n_large; ++i) {  // dispatch order (largest first) inside a class
+      if (class_of(pl->large_free[i]) != cls) continue;
+      const uint32_t c = pl->large_slots[i];
+      const uint32_t nc = p->comp_ptr[c + 1] - p->comp_ptr[c];
+      if (pl->large_cand[i] > 0xffffffffull) return fail(LFR_EUNSUPPORTED, "component with more than 2^32 out-edges");
+      lfr::CtaComp& cc = comps[k];
+      cc.slot = c;
+      cc.Nc = nc;
+      cc.Ec = 0;  // filled on the device, with nf and regular
+      cc.nf = 0;
+      cc.regular = 0;
+      cc.e_off = e_off;
+      cc.n_off = n_off;
+      cc.f_off = f_off;
+      cc.comp_index = k;
+      cc.ell_off = ell_off;
+      cc.s_off = s_off;
+      ell_off += pl->large_ell[i];
+      s_off += (nc + 31) / 32 + 1;
+      g.max_free = std::max(g.max_free, pl->large_free[i]);
+      pl->L_max_free = std::max(pl->L_max_free, pl->large_free[i]);
+      e_off += pl->large_cand[i];
+      n_off += nc;
+      f_off += pl->large_free[i];
+      ++k;
     }
-    const uint32_t ec = (uint32_t)(eidx.size() - e0);
-    // in-edge lists: counting sort by destination (stable => ascending edge index)
-    std::vector<uint32_t> ip(nc + 1, 0);
-    for (uint32_t l = 0; l < nc; ++l) ip[l + 1] = ip[l] + cin[l];
-    std::vector<uint32_t> fill(ip.begin(), ip.end() - 1);
-    inlist.resize(e0 + ec);
-    for (uint32_t j = 0; j < ec; ++j) {
-      const uint32_t dl = (meta[e0 + j] >> 14) & 0x3fff;
-      inlist[e0 + fill[dl]++] = j;
-    }
-    inptr.insert(inptr.end(), ip.begin(), ip.end());
-    uint32_t nf = 0;
-    for (uint32_t l = 0; l < nc; ++l) {
-      const bool is_free = (cout[l] + cin[l] > 0) && !p->is_root[p->comp_nodes[beg + l]];
-      freeof.push_back(is_free ? (int32_t)nf : -1);
-      if (is_free) {
-        lof.push_back(l);
-        ++nf;
-      }
-    }
-    for (uint32_t l = 0; l < nc; ++l) local[p->comp_nodes[beg + l]] = -1;
-    // twin (reverse edge) of every kept edge and the destination's free index
-    bool regular = true;
-    twin.resize(e0 + ec);
-    fdst.resize(e0 + ec);
-    const size_t op0 = outptr.size() - (nc + 1), fo0 = freeof.size() - nc;
-    for (uint32_t j = 0; j < ec; ++j) {
-      const uint32_t sl = meta[e0 + j] & 0x3fff, dl = (meta[e0 + j] >> 14) & 0x3fff;
-      uint32_t found = 0, tw = j;
-      for (uint32_t t = outptr[op0 + dl]; t < outptr[op0 + dl + 1]; ++t)
-        if (((meta[e0 + t] >> 14) & 0x3fff) == sl) {
-          tw = t;
-          ++found;
-        }
-      if (found != 1) regular = false;
-      twin[e0 + j] = tw;
-      fdst[e0 + j] = freeof[fo0 + dl];
-    }
-    lfr::CtaComp& cc = comps[k];
-    cc.slot = c;
-    cc.Nc = nc;
-    cc.Ec = ec;
-    cc.nf = nf;
-    cc.regular = regular ? 1u : 0u;
-    cc.e_off = e_off;
-    cc.n_off = n_off;
-    cc.f_off = f_off;
-    cc.comp_index = k;
-    pl->L_max_free = std::max(pl->L_max_free, nf);
-    e_off += ec;
-    n_off += nc;
-    f_off += nf;
+    g.n = k - g.first;
+    if (g.n) pl->cta_groups.push_back(g);
   }
   pl->L_total_free = f_off;
+  const uint64_t E1 = std::max<uint64_t>(e_off, 1), N1 = std::max<uint64_t>(n_off, 1), F1 = std::max<uint64_t>(f_off, 1);
+  const uint64_t L1 = std::max<uint64_t>(ell_off, 1), S1 = std::max<uint64_t>(s_off, 1);
   LFR_TRY(upload(&pl->L_comps, comps.data(), comps.size(), s));
-  LFR_TRY(upload(&pl->L_eidx, eidx.data(), eidx.size(), s));
-  LFR_TRY(upload(&pl->L_meta, meta.data(), meta.size(), s));
-  LFR_TRY(upload(&pl->L_inlist, inlist.data(), inlist.size(), s));
-  LFR_TRY(upload(&pl->L_twin, twin.data(), twin.size(), s));
-  LFR_TRY(upload(&pl->L_fdst, fdst.data(), fdst.size(), s));
-  LFR_TRY(pl->L_bmat.reserve(sizeof(double) * 4 * std::max<uint64_t>(e_off, 1)));
-  LFR_TRY(upload(&pl->L_node, node.data(), node.size(), s));
-  LFR_TRY(upload(&pl->L_outptr, outptr.data(), outptr.size(), s));
-  LFR_TRY(upload(&pl->L_inptr, inptr.data(), inptr.size(), s));
-  LFR_TRY(upload(&pl->L_freeof, freeof.data(), freeof.size(), s));
-  LFR_TRY(upload(&pl->L_lof, lof.data(), lof.size(), s));
-  LFR_TRY(pl->L_scr.reserve(sizeof(double) * 7 * std::max<uint64_t>(e_off, 1)));
-  LFR_TRY(pl->L_q.reserve(sizeof(double) * 2 * std::max<uint64_t>(e_off, 1)));
-  LFR_TRY(pl->L_x.reserve(sizeof(double) * 2 * std::max<uint64_t>(n_off, 1)));
-  LFR_TRY(pl->L_xc.reserve(sizeof(double) * 2 * std::max<uint64_t>(n_off, 1)));
-  LFR_TRY(pl->L_vec.reserve(sizeof(double) * (2 * lfr::V_COUNT + 9) * std::max<uint64_t>(f_off, 1)));
-  // the upload sources above are locals: make sure the copies are done before they go away
-  LFR_CUDA(cudaStreamSynchronize(s));
+  LFR_TRY(pl->L_rec.reserve(sizeof(float4) * 5 * E1));
+  LFR_TRY(pl->L_meta.reserve(sizeof(uint32_t) * E1));
+  LFR_TRY(pl->L_inlist.reserve(sizeof(uint32_t) * E1));
+  LFR_TRY(pl->L_twin.reserve(sizeof(uint32_t) * E1));
+  LFR_TRY(pl->L_fdst.reserve(sizeof(int32_t) * E1));
+  LFR_TRY(pl->L_bE01.reserve(sizeof(double2) * L1));
+  LFR_TRY(pl->L_bE23.reserve(sizeof(double2) * L1));
+  LFR_TRY(pl->L_fdstE.reserve(sizeof(int32_t) * L1));
+  LFR_TRY(pl->L_ell_base.reserve(sizeof(uint32_t) * S1));
+  LFR_TRY(pl->L_node.reserve(sizeof(uint32_t) * N1));
+  LFR_TRY(pl->L_outptr.reserve(sizeof(uint32_t) * (N1 + pl->n_large)));
+  LFR_TRY(pl->L_inptr.reserve(sizeof(uint32_t) * (N1 + pl->n_large)));
+  LFR_TRY(pl->L_freeof.reserve(sizeof(int32_t) * N1));
+  LFR_TRY(pl->L_lof.reserve(sizeof(uint32_t) * F1));
+  LFR_TRY(pl->L_scr.reserve(sizeof(double) * 7 * E1));
+  LFR_TRY(pl->L_q.reserve(sizeof(double) * 2 * E1));
+  LFR_TRY(pl->L_x.reserve(sizeof(double) * 2 * N1));
+  LFR_TRY(pl->L_xc.reserve(sizeof(double) * 2 * N1));
+  LFR_TRY(pl->L_vec.reserve(sizeof(double) * (2 * lfr::V_COUNT + 9) * F1));
   return LFR_OK;
 }
 
@@ -551,10 +615,12 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
       LFR_CUDA(cudaMemsetAsync(pl->pos_init.p, 0, sizeof(double) * 2 * N, s));
     pl->pos_is_staged = false;
   }
+  host_mark(0);
   LFR_TRY(build_buckets(pl, p));  // host work overlaps the copies above
+  host_mark(1);
   if (zc_edges && pl->needs_hbm_edges) {
-    // mixed schedule: the Cholesky-warp / CTA tiers read edges from global memory by index, so the
-    // array goes to HBM after all — on its own stream, and only those tiers wait for it
+    // mixed schedule: the Cholesky-warp tier reads edge records from global memory by index, so the
+    // array goes to HBM after all — on its own stream, and only that tier waits for it
     if (!pl->copy_stream) LFR_CUDA(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
     if (!pl->ev_edges) LFR_CUDA(cudaEventCreateWithFlags(&pl->ev_edges, cudaEventDisableTiming));
     LFR_TRY(upload(&pl->edges, p->edges, (size_t)p->n_edges, pl->copy_stream));
@@ -569,8 +635,17 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
         pl->local_of.as<uint32_t>());
     LFR_CUDA(cudaGetLastError());
   }
+  if (pl->n_large) {
+    // kept-edge records / in-edge lists, free-variable numbering and twins of the CTA-tier components,
+    // built on the device; with zero-copy edges the kernel pulls exactly the records these
+    // components keep from the caller's pinned array (no bulk copy of the edge array)
+    lfr::DevProblem P = pl->dev();
+    if (zc_edges) P.edges = zc_edges;
+    lfr::cta_prepare_kernel<<<pl->n_large, lfr::kCtaThreads, 0, s>>>(P, pl->cta_arrays(), pl->L_comps.as<lfr::CtaComp>());
+    LFR_CUDA(cudaGetLastError());
+  }
   // streams for concurrent bucket launches
-  const int want = std::min<int>(kMaxStreams, std::max<int>(0, (int)pl->buckets.size() - 1 + (pl->n_large ? 1 : 0)));
+  const int want = std::min<int>(kMaxStreams, std::max<int>(0, (int)pl->buckets.size() + (int)pl->cta_groups.size() - 1));
   if (!pl->ev_fork) LFR_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
   while (pl->n_streams < want) {
     LFR_CUDA(cudaStreamCreateWithFlags(&pl->streams[pl->n_streams], cudaStreamNonBlocking));
@@ -580,12 +655,26 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
   return LFR_OK;
 }
 
+// Bytes of zero-copy staging pulls kept outstanding per device (stage_edges): large enough to cover
+// the PCIe bandwidth-delay product, small enough that records arrive in dispatch order.
+// LFR_PULL_WINDOW_KB overrides (0 = unpaced), read once.
+unsigned zero_copy_pull_window() {
+  static const unsigned w = [] {
+    const char* e = std::getenv("LFR_PULL_WINDOW_KB");
+    if (e && *e) return (unsigned)std::strtoul(e, nullptr, 10) * 1024u;
+    return 512u * 1024u;
+  }();
+  return w;
+}
+
 int set_kernel_attrs() {
   static bool done_for_device[16] = {};  // per device, guarded by that device's workspace mutex / idempotent otherwise
   int dev = 0;
   LFR_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 16 && done_for_device[dev]) return LFR_OK;
-  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -620,42 +709,36 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
   pl->pos_is_staged = false;  // a second launch on the same plan needs the reset again
   const lfr::DevProblem P_hbm = pl->dev();  // edges read from the HBM copy by global index
   lfr::DevProblem P_stage = P_hbm;          // edges pulled once into shared memory, possibly from the caller's pinned buffer
-  if (pl->zc_edges) P_stage.edges = pl->zc_edges;
+  if (pl->zc_edges) {
+    P_stage.edges = pl->zc_edges;
+    P_stage.pull_window = zero_copy_pull_window();
+  }
   const bool hbm_edges_on_copy_stream = pl->zc_edges && pl->edges_in_hbm;
   const int nb = (int)pl->buckets.size();
-  const int n_side = std::max(0, nb - 1) + ((pl->n_large && nb > 0) ? 1 : 0);
+  const int n_cta_launches = pl->n_large ? (int)pl->cta_groups.size() : 0;
+  const int n_side = std::max(0, nb + n_cta_launches - 1);
   if (n_side > 0) LFR_CUDA(cudaEventRecord(pl->ev_fork, s));
   int side = 0;
   if (pl->n_large) {  // the CTA tier first: its components are the longest
-    cudaStream_t bs = s;
-    if (nb > 0) {
-      bs = pl->streams[side++ % pl->n_streams];
-      LFR_CUDA(cudaStreamWaitEvent(bs, pl->ev_fork, 0));
+    const lfr::CtaArrays A = pl->cta_arrays();
+    for (const CtaGroup& g : pl->cta_groups) {
+      cudaStream_t bs = s;
+      if (n_side > 0) {
+        bs = pl->streams[side++ % pl->n_streams];
+        LFR_CUDA(cudaStreamWaitEvent(bs, pl->ev_fork, 0));
+      }
+      // dynamic shared memory for the CG vectors of the group's largest component (13 doubles per free node)
+      const size_t cg_bytes = std::min<size_t>(200 * 1024, (size_t)g.max_free * 13 * sizeof(double));
+      const lfr::CtaComp* comps = pl->L_comps.as<lfr::CtaComp>() + g.first;
+      const unsigned smem_doubles = (unsigned)(cg_bytes / sizeof(double));
+      if (g.minb >= 4)
+        lfr::solve_cta_kernel<4><<<g.n, lfr::kCtaThreads, cg_bytes, bs>>>(P_hbm, pl->K, A, comps, smem_doubles);
+      else if (g.minb == 3)
+        lfr::solve_cta_kernel<3><<<g.n, lfr::kCtaThreads, cg_bytes, bs>>>(P_hbm, pl->K, A, comps, smem_doubles);
+      else
+        lfr::solve_cta_kernel<2><<<g.n, lfr::kCtaThreads, cg_bytes, bs>>>(P_hbm, pl->K, A, comps, smem_doubles);
+      LFR_CUDA(cudaGetLastError());
     }
-    lfr::CtaArrays A;
-    A.eidx = pl->L_eidx.as<uint32_t>();
-    A.meta = pl->L_meta.as<uint32_t>();
-    A.inlist = pl->L_inlist.as<uint32_t>();
-    A.twin = pl->L_twin.as<uint32_t>();
-    A.fdst = pl->L_fdst.as<int32_t>();
-    A.bmat = pl->L_bmat.as<double>();
-    A.scr = pl->L_scr.as<double>();
-    A.q = pl->L_q.as<double>();
-    A.node = pl->L_node.as<uint32_t>();
-    A.outptr = pl->L_outptr.as<uint32_t>();
-    A.inptr = pl->L_inptr.as<uint32_t>();
-    A.freeof = pl->L_freeof.as<int32_t>();
-    A.x = pl->L_x.as<double>();
-    A.xc = pl->L_xc.as<double>();
-    A.lof = pl->L_lof.as<uint32_t>();
-    A.vec = pl->L_vec.as<double>();
-    A.total_free = pl->L_total_free;
-    if (hbm_edges_on_copy_stream) LFR_CUDA(cudaStreamWaitEvent(bs, pl->ev_edges, 0));
-    // dynamic shared memory for the CG vectors of the largest component of this launch (13 doubles per free node)
-    const size_t cg_bytes = std::min<size_t>(200 * 1024, (size_t)pl->L_max_free * 13 * sizeof(double));
-    lfr::solve_cta_kernel<<<pl->n_large, lfr::kCtaThreads, cg_bytes, bs>>>(P_hbm, pl->K, A, pl->L_comps.as<lfr::CtaComp>(),
-                                                                          (unsigned)(cg_bytes / sizeof(double)));
-    LFR_CUDA(cudaGetLastError());
   }
   for (int i = 0; i < nb; ++i) {
     const Bucket& b = pl->buckets[i];
@@ -749,7 +832,7 @@ int download(lfr_plan* pl, cudaStream_t s, double* positions, lfr_stats* st) {
     st->total_iterations = ti;
     st->total_line_search_steps = tl;
     st->n_solved = pl->n_solved;
-    st->n_kernel_launches = (uint32_t)pl->buckets.size() + (pl->n_large ? 1u : 0u);
+    st->n_kernel_launches = (uint32_t)pl->buckets.size() + (uint32_t)pl->cta_groups.size();
   }
   return LFR_OK;
 }
@@ -803,11 +886,14 @@ int solve_on_device(const lfr_problem* p, const lfr_options& o, double* position
   const bool zero_copy = !(o.debug_flags & LFR_DBG_NO_ZERO_COPY);
   const float4* zc_edges = (zero_copy && p->n_edges) ? static_cast<const float4*>(device_view_of_pinned(p->edges)) : nullptr;
   double* zc_positions = (zero_copy && p->n_nodes) ? static_cast<double*>(device_view_of_pinned(positions)) : nullptr;
+  g_host_t0 = std::chrono::steady_clock::now();
   LFR_CUDA(cudaEventRecord(ws.ev[0], s));
   LFR_TRY(fill_plan(pl, p, o, positions, s, /*stage_positions_directly=*/true, zc_edges, zc_positions));
+  host_mark(2);
   LFR_CUDA(cudaEventRecord(ws.ev[1], s));
   LFR_TRY(launch_solve(pl, s));
   LFR_CUDA(cudaEventRecord(ws.ev[2], s));
+  host_mark(3);
   // several devices, pageable positions: each device returns its copy into its own scratch array
   // and the caller merges the entries of the components it owns
   int rc = download(pl, s, (slot_owner && !zc_positions) ? pos_scratch : positions, st);
@@ -816,10 +902,12 @@ int solve_on_device(const lfr_problem* p, const lfr_options& o, double* position
     cudaError_t e = cudaStreamSynchronize(pl->copy_stream);
     if (e != cudaSuccess && rc == LFR_OK) rc = fail(cuda_code(e), cudaGetErrorString(e));
   }
+  host_mark(4);
   pl->slot_owner = nullptr;
   if (rc) return rc;
   LFR_CUDA(cudaEventRecord(ws.ev[3], s));
   LFR_CUDA(cudaEventSynchronize(ws.ev[3]));
+  host_mark(5);
   if (st) {
     float a = 0, b = 0, c = 0;
     cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]);
@@ -900,7 +988,7 @@ int lfr_plan_solve(lfr_plan* pl, void* stream) {
 
 int lfr_plan_num_launches(const lfr_plan* pl) {
   // kernels only: the device-to-device reset of `positions` is a copy, not a kernel
-  return pl ? (int)pl->buckets.size() + (pl->n_large ? 1 : 0) : 0;
+  return pl ? (int)pl->buckets.size() + (int)pl->cta_groups.size() : 0;
 }
 
 int lfr_plan_download(lfr_plan* pl, void* stream, double* positions, lfr_stats* st) {
@@ -938,6 +1026,13 @@ int lfr_debug_plan_cycles(lfr_plan* pl, unsigned long long* out) {
   return LFR_OK;
 }
 
+int lfr_debug_plan_times(lfr_plan* pl, unsigned long long* out) {
+  if (!pl || !pl->profile) return fail(LFR_EINVAL, "plan was not created with LFR_DBG_PROFILE");
+  LFR_CUDA(cudaSetDevice(pl->device));
+  LFR_CUDA(cudaMemcpy(out, pl->times.p, sizeof(unsigned long long) * 2 * (size_t)pl->C, cudaMemcpyDeviceToHost));
+  return LFR_OK;
+}
+
 /* debug (LFR_DBG_PROFILE): counters of the last lfr_solve() of this thread on `device`:
    cycles [8 per slot], times [2 per slot] = %globaltimer ns at start / end of each component */
 int lfr_debug_last_solve_profile(int device, unsigned long long* cycles, unsigned long long* times) {
@@ -947,6 +1042,49 @@ int lfr_debug_last_solve_profile(int device, unsigned long long* cycles, unsigne
   LFR_CUDA(cudaSetDevice(device));
   if (cycles) LFR_CUDA(cudaMemcpy(cycles, pl->cycles.p, sizeof(unsigned long long) * 8 * (size_t)pl->C, cudaMemcpyDeviceToHost));
   if (times) LFR_CUDA(cudaMemcpy(times, pl->times.p, sizeof(unsigned long long) * 2 * (size_t)pl->C, cudaMemcpyDeviceToHost));
+  return LFR_OK;
+}
+
+// host-only: best-of-`reps` time of the schedule construction (build_buckets), no device needed
+int lfr_debug_time_schedule(const lfr_problem* p, const lfr_options* opt, int reps, double* best_us, int* n_launches) {
+  if (!p || !best_us) return fail(LFR_EINVAL, "null argument");
+  LFR_TRY(validate(p));
+  lfr_plan pl;
+  if (opt) pl.opt = *opt; else lfr_options_default(&pl.opt);
+  pl.N = p->n_nodes;
+  pl.C = p->n_components;
+  pl.total_slots = p->n_components ? p->comp_ptr[p->n_components] : 0;
+  double best = 1e300;
+  for (int r = 0; r < std::max(reps, 1); ++r) {
+    const auto t0 = std::chrono::steady_clock::now();
+    LFR_TRY(build_buckets(&pl, p));
+    best = std::min(best, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+  }
+  if (std::getenv("LFR_SCHED_SPLIT")) {  // diagnostic: the node loop alone
+    double b2 = 1e300;
+    uint64_t sink = 0;
+    for (int r = 0; r < std::max(reps, 1); ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (uint32_t c = 0; c < p->n_components; ++c) {
+        uint64_t eup = 0; uint32_t nfree = 0;
+        for (uint32_t i = p->comp_ptr[c]; i < p->comp_ptr[c + 1]; ++i) {
+          const uint32_t v = p->comp_nodes[i];
+          eup += p->row_ptr[v + 1] - p->row_ptr[v];
+          nfree += p->is_root[v] ? 0 : 1;
+        }
+        sink += eup * 3 + nfree;
+      }
+      b2 = std::min(b2, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    }
+    std::fprintf(stderr, "node loop alone %.1f us (sink %llu)\n", b2, (unsigned long long)sink);
+  }
+  *best_us = best;
+  if (n_launches) *n_launches = (int)pl.buckets.size() + (pl.large_slots.empty() ? 0 : 1);  // (CTA tier counted once here)
+  return LFR_OK;
+}
+
+int lfr_debug_last_host_marks(double* out6) {
+  for (int i = 0; i < 6; ++i) out6[i] = g_host_marks[i];
   return LFR_OK;
 }
 

@@ -35,6 +35,8 @@ struct DevProblem {
   double* positions;         // [2N] start point (device memory)
   double* positions_out;     // [2N] results: `positions` itself, or the caller's pinned host buffer
                              // (zero-copy write-back: only free nodes are written, solve.cc:131-141)
+  unsigned long long* pull_ctr;  // [2] bytes of staging pulls {ticketed, arrived} (zero-copy pacing, see stage_edges)
+  unsigned pull_window;      // 0 = unpaced; else at most this many bytes of staging pulls are outstanding per device
   int stage_mode;            // how the staging tiers pull a component's edge records into shared memory:
                              // 1 = TMA 1-D bulk copies (cp.async.bulk + mbarrier), 0 = LDG -> STS
   // per dispatch slot

@@ -487,6 +487,19 @@ __device__ __forceinline__ void stage_edges(Ctx& C, const uint32_t* rowstart, co
                                             int Eup, const DevProblem& P, int lane) {
   if (Eup == 0) return;
   if (P.stage_mode == 1) {
+    // Pacing of zero-copy pulls: every resident warp asking for its records at once makes the PCIe
+    // link serve ~10 MB of requests round-robin, so the FIRST components (the largest, dispatched
+    // first because they run longest) get their data last.  A ticket counter keeps at most
+    // `pull_window` bytes outstanding: records arrive in dispatch order at the same link rate.
+    const bool paced = P.pull_window != 0;
+    if (paced) {
+      if (lane == 0) {
+        const unsigned long long ticket = atomicAdd(P.pull_ctr, 80ull * (unsigned)Eup);
+        const volatile unsigned long long* arrived = P.pull_ctr + 1;
+        while ((long long)(ticket - *arrived) >= (long long)P.pull_window) __nanosleep(64);
+      }
+      __syncwarp();
+    }
     if (lane == 0) mbar_arrive_expect_tx(C.bar, 80u * (uint32_t)Eup);
     __syncwarp();
     for (int l = lane; l < Nc; l += 32) {
@@ -494,6 +507,7 @@ __device__ __forceinline__ void stage_edges(Ctx& C, const uint32_t* rowstart, co
       if (d) bulk_copy_g2s(C.stage + 5 * candptr[l], P.edges + 5 * (size_t)rowstart[l], 80u * d, C.bar);
     }
     mbar_wait(C.bar, 0);
+    if (paced && lane == 0) atomicAdd(P.pull_ctr + 1, 80ull * (unsigned)Eup);
   } else {
     // LDG -> STS, lane-linear over the 16-byte words, four loads in flight per lane
     const int W = 5 * Eup;

@@ -1,0 +1,64 @@
+"""cfg5, one GPU, plan path with LFR_DBG_PROFILE: per-component start / end (%globaltimer) and SM of
+the CTA tier for consecutive solves — why is the same solve 382 ms one time and 541 ms the next?"""
+import ctypes as C
+import os
+import sys
+
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R)
+import numpy as np  # noqa: E402
+
+from lfr_b200 import build_problem, synth  # noqa: E402
+from lfr_b200.capi import Plan, load_b200  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg5"
+n_solves = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+p = build_problem(synth.generate(name))
+lib = load_b200()
+import torch  # noqa: E402
+
+plan = Plan(lib, p, lib.default_options(debug_flags=0x10))
+s = torch.cuda.current_stream().cuda_stream
+sizes = np.diff(p.comp_ptr.astype(np.int64))
+Cn = p.n_components
+fc = lib.lib.lfr_debug_plan_cycles
+ft = lib.lib.lfr_debug_plan_times
+fc.argtypes = [C.c_void_p, C.c_void_p]
+ft.argtypes = [C.c_void_p, C.c_void_p]
+for i in range(n_solves):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    plan.solve(s)
+    e1.record()
+    torch.cuda.synchronize()
+    cyc = np.zeros((Cn, 8), dtype=np.uint64)
+    tm = np.zeros((Cn, 2), dtype=np.uint64)
+    assert fc(plan.handle, cyc.ctypes.data) == 0 and ft(plan.handle, tm.ctypes.data) == 0
+    ran = tm[:, 0] > 0
+    t0 = tm[ran, 0].min()
+    st = (tm[:, 0].astype(np.float64) - t0) / 1e6
+    en = (tm[:, 1].astype(np.float64) - t0) / 1e6
+    dur = en - st
+    cta = ran & (cyc[:, 1] == 1)
+    print("solve %d: %.1f ms by events; components timed %d (CTA tier %d); last end %.1f ms" % (
+        i, e0.elapsed_time(e1), int(ran.sum()), int(cta.sum()), en[ran].max()))
+    if cta.any():
+        sm = cyc[cta, 7].astype(np.int64)
+        print("   CTA tier: sum of durations %.0f ms over %d SMs -> /296 = %.1f ms;  start p50 %.1f p90 %.1f max %.1f;  duration p50 %.2f p99 %.1f max %.1f" % (
+            dur[cta].sum(), len(np.unique(sm)), dur[cta].sum() / 296.0, np.median(st[cta]), np.percentile(st[cta], 90), st[cta].max(),
+            np.median(dur[cta]), np.percentile(dur[cta], 99), dur[cta].max()))
+        idx = np.where(cta)[0]
+        order = idx[np.argsort(-en[idx])[:5]]
+        for k in order:
+            print("     slot %5d nodes %4d start %7.1f dur %7.1f end %7.1f  sm %3d  cg_iters %d  lm %d" % (
+                k, sizes[k], st[k], dur[k], en[k], int(cyc[k, 7]), int(cyc[k, 4]), int(cyc[k, 3])))
+        # concurrency: CTA-tier components running at a few instants
+        for t in (5, 50, 100, 200, 300, 350, 400, 500):
+            print("     t=%3d ms running %d" % (t, int(((st[cta] <= t) & (en[cta] > t)).sum())), end="")
+        print()
+        # per-SM busy time
+        busy = np.bincount(sm, weights=dur[cta], minlength=148)
+        print("   per-SM sum of durations: min %.0f p50 %.0f max %.0f" % (busy.min(), np.median(busy), busy.max()))
+    oth = ran & ~cta
+    if oth.any():
+        print("   other tiers: %d components, start p50 %.1f max %.1f, end max %.1f" % (int(oth.sum()), np.median(st[oth]), st[oth].max(), en[oth].max()))
