@@ -121,6 +121,7 @@ struct DevBuf {
 struct CtaGroup {
   uint32_t first = 0, n = 0, max_free = 0;
   int minb = 2;
+  int smem_vecs = 6;  // how many of the CG arrays (p, w, r, z, y, preconditioner) live in shared memory
 };
 
 struct Bucket {
@@ -361,7 +362,7 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
       for (uint32_t i0 = beg; i0 < end; i0 += 32) {
         uint32_t wmax = 0;
         for (uint32_t i = i0; i < std::min(end, i0 + 32); ++i) wmax = std::max(wmax, row_ptr[comp_nodes[i] + 1] - row_ptr[comp_nodes[i]]);
-        slots += 32ull * wmax;
+        slots += 32ull * ((wmax + 3u) & ~3u);  // slice width: a multiple of four slots (cta_block_row)
       }
       if (slots > 0xffffffffull) return fail(LFR_EUNSUPPORTED, "component too dense for the CTA tier's block layout");
       pl->large_ell.push_back(slots);
@@ -470,6 +471,12 @@ int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
     if (std::sscanf(e, "%d,%d,%d,%d", &a[0], &a[1], &a[2], &a[3]) == 4)
       for (int i = 0; i < 4; ++i) minb[i] = std::min(4, std::max(2, a[i]));
   }
+  int smem_vecs[4] = {6, 6, 6, 6};
+  if (const char* e = std::getenv("LFR_CTA_SMEM_VECS")) {  // tuning hook: "6,6,6,6"
+    int a[4];
+    if (std::sscanf(e, "%d,%d,%d,%d", &a[0], &a[1], &a[2], &a[3]) == 4)
+      for (int i = 0; i < 4; ++i) smem_vecs[i] = std::min(6, std::max(0, a[i]));
+  }
   auto class_of = [&](uint32_t nfree) { return nfree > kClassMaxFree[1] ? 0 : (nfree > kClassMaxFree[2] ? 1 : (nfree > kClassMaxFree[3] ? 2 : 3)); };
   pl->cta_groups.clear();
   uint64_t e_off = 0, n_off = 0, f_off = 0, ell_off = 0, s_off = 0;
@@ -478,6 +485,7 @@ int prepare_large(lfr_plan* pl, const lfr_problem* p, cudaStream_t s) {
     CtaGroup g;
     g.first = k;
     g.minb = minb[cls];
+    g.smem_vecs = smem_vecs[cls];
     for (uint32_t i = 0; i < pl->n_large; ++i) {  // dispatch order (largest first) inside a class
       if (class_of(pl->large_free[i]) != cls) continue;
       const uint32_t c = pl->large_slots[i];
@@ -727,8 +735,10 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
         bs = pl->streams[side++ % pl->n_streams];
         LFR_CUDA(cudaStreamWaitEvent(bs, pl->ev_fork, 0));
       }
-      // dynamic shared memory for the CG vectors of the group's largest component (13 doubles per free node)
-      const size_t cg_bytes = std::min<size_t>(200 * 1024, (size_t)g.max_free * 13 * sizeof(double));
+      // dynamic shared memory for the CG vectors of the group's largest component: the first
+      // `smem_vecs` of p, w, r, z, y (2 doubles per free node each) and the preconditioner (3)
+      const size_t per_node = (size_t)std::min(g.smem_vecs, 5) * 2 + (g.smem_vecs >= 6 ? 3 : 0);
+      const size_t cg_bytes = std::min<size_t>(200 * 1024, (size_t)g.max_free * per_node * sizeof(double));
       const lfr::CtaComp* comps = pl->L_comps.as<lfr::CtaComp>() + g.first;
       const unsigned smem_doubles = (unsigned)(cg_bytes / sizeof(double));
       if (g.minb >= 4)

@@ -59,6 +59,8 @@ constexpr int kCtaThreads = 256;
 enum { V_G = 0, V_S, V_DL, V_D2, V_R, V_Z, V_P, V_W, V_Y, V_COUNT };  // 2-doubles-per-node vectors
 // then three 3-doubles-per-node arrays: diagonal blocks (d00, d01, d11), their damped scaled form, its inverse
 
+constexpr int kCtaRowsCached = 4;  // covers components up to 1024 nodes (solve.cc:586 caps them at #images)
+
 struct CtaCtx {
   int tid, Nc, Ec, nf, n;
   const uint32_t *meta, *inlist, *node, *outptr, *inptr, *lof;
@@ -67,11 +69,14 @@ struct CtaCtx {
   double2 *bE01, *bE23;
   const int32_t* fdstE;
   const uint32_t* ell_base;
+  int row_f[kCtaRowsCached];        // block rows tid, tid + 256, ...: free index (-1: none), degree, first ELL slot
+  uint32_t row_deg[kCtaRowsCached], row_slot[kCtaRowsCached];
   const uint32_t* twin;
   const int32_t* fdst;
   bool regular;
   const float4* rec;
-  double* red;  // shared: 3 * 8 doubles
+  double* red;   // shared: 3 * 8 doubles
+  double* red2;  // shared: 2 parities x 2 values x 8 warps (block_sum_db)
 };
 
 __device__ __forceinline__ double2* P2(double* p) { return reinterpret_cast<double2*>(p); }  // per-node pairs are 16-byte aligned
@@ -99,6 +104,33 @@ __device__ __forceinline__ void block_sum3(const CtaCtx& C, double& a, double& b
     c += C.red[2 * nw + i];
   }
 }
+// N sums with ONE barrier: partials go to the `parity` half of a double-buffered line, so the next
+// call (other parity) may write while stragglers still read this one; calls with the same parity
+// must be separated by another barrier (the CG loop alternates 0, 1 and ends each iteration with one).
+template <int N>
+__device__ __forceinline__ void block_sum_db(const CtaCtx& C, double (&v)[N], int parity) {
+  static_assert(N <= 2, "red2 holds two values per warp and parity");
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] += __shfl_xor_sync(kFull, v[k], o);
+  }
+  constexpr int nw = kCtaThreads / 32;
+  double* line = C.red2 + parity * 2 * nw;
+  if ((C.tid & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) line[k * nw + (C.tid >> 5)] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < nw; ++i) a += line[k * nw + i];  // fixed order: identical in every thread, reproducible
+    v[k] = a;
+  }
+}
+
 __device__ __forceinline__ double block_max(const CtaCtx& C, double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
@@ -261,30 +293,54 @@ __device__ __forceinline__ void cta_matvec(const CtaCtx& C, const double* v, dou
 // warp's k-th loads (destination index, two 16-byte halves of the block) are each ONE contiguous
 // 128 / 512-byte access.  ncu (round 2, cfg5): with the blocks in CSR order every lane strode through
 // its own row — L1/TEX at 85 % of peak on uncoalesced 8-byte loads bounded the whole tier.
+// One block row: w_f = P_f v_f + sum_k B_k v_col(k), blocks k = 0 .. deg-1 at slot0 + 32 k.
+// The row is walked in groups of four slots with NO branch on the column index: a slot past the row's
+// end, or whose column is a root, holds a zero block and column -1 (the preparation kernel fills
+// every slot of the slice, whose width is a multiple of 4), so the twelve loads of a group — four
+// column indices, eight block halves — are all in flight before the first one is needed, and a
+// group costs one L2 round trip (+ the shared-memory gathers) instead of one per block.
+__device__ __forceinline__ double cta_block_row(const CtaCtx& C, const double2* v2, double2* w2, const double* pblk,
+                                                int f, uint32_t deg, size_t s) {
+  const double2 vv = v2[f];
+  double a0 = pblk[3 * f] * vv.x + pblk[3 * f + 1] * vv.y, a1 = pblk[3 * f + 1] * vv.x + pblk[3 * f + 2] * vv.y;
+  for (uint32_t k = 0; k < deg; k += 4, s += 128) {
+    int fd[4];
+    double2 b01[4], b23[4], u[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      fd[t] = C.fdstE[s + 32 * t];
+      b01[t] = C.bE01[s + 32 * t];
+      b23[t] = C.bE23[s + 32 * t];
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) u[t] = v2[max(fd[t], 0)];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {  // same order as a slot-by-slot walk; a zero block adds +0.0
+      a0 += b01[t].x * u[t].x + b01[t].y * u[t].y;
+      a1 += b23[t].x * u[t].x + b23[t].y * u[t].y;
+    }
+  }
+  w2[f] = make_double2(a0, a1);
+  return vv.x * a0 + vv.y * a1;
+}
+
+template <bool SYNC = true>
 __device__ __forceinline__ double cta_matvec_bcsr(const CtaCtx& C, const double* v, double* w, const double* pblk) {
   const double2* v2 = reinterpret_cast<const double2*>(v);
   double2* w2 = reinterpret_cast<double2*>(w);
   double dot = 0.0;
-  for (int l = C.tid; l < C.Nc; l += kCtaThreads) {
+  // the first kCtaRowsCached rows of this thread: free index, degree and first slot sit in registers
+  // (they never change), which takes two dependent L2 round trips out of every CG iteration
+#pragma unroll
+  for (int i = 0; i < kCtaRowsCached; ++i)
+    if (C.row_f[i] >= 0) dot += cta_block_row(C, v2, w2, pblk, C.row_f[i], C.row_deg[i], C.row_slot[i]);
+  for (int l = C.tid + kCtaRowsCached * kCtaThreads; l < C.Nc; l += kCtaThreads) {
     const int f = C.freeof[l];
     if (f < 0) continue;
-    const double2 vv = v2[f];
-    double a0 = pblk[3 * f] * vv.x + pblk[3 * f + 1] * vv.y, a1 = pblk[3 * f + 1] * vv.x + pblk[3 * f + 2] * vv.y;
-    const uint32_t deg = C.outptr[l + 1] - C.outptr[l];
-    size_t s = (size_t)C.ell_base[l >> 5] + (uint32_t)(l & 31);
-#pragma unroll 4
-    for (uint32_t k = 0; k < deg; ++k, s += 32) {
-      const int fd = C.fdstE[s];
-      if (fd < 0) continue;
-      const double2 b01 = C.bE01[s], b23 = C.bE23[s];
-      const double2 u = v2[fd];
-      a0 += b01.x * u.x + b01.y * u.y;
-      a1 += b23.x * u.x + b23.y * u.y;
-    }
-    w2[f] = make_double2(a0, a1);
-    dot += vv.x * a0 + vv.y * a1;
+    dot += cta_block_row(C, v2, w2, pblk, f, C.outptr[l + 1] - C.outptr[l],
+                         (size_t)C.ell_base[l >> 5] + (uint32_t)(l & 31));
   }
-  __syncthreads();
+  if (SYNC) __syncthreads();  // (else the caller's reduction barrier publishes w)
   return dot;
 }
 
@@ -292,7 +348,7 @@ __device__ __forceinline__ double cta_matvec_bcsr(const CtaCtx& C, const double*
 // {model_cost_change, g . dl, |dl|_inf}.
 __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, const DevConsts& K, double* model_change,
                                             double* gd, double* dmax, unsigned* cg_iters, bool diag_mode,
-                                            double* worst_res, unsigned* n_maxit) {
+                                            double* worst_res, unsigned* n_maxit, long long* tph = nullptr) {
   // damping, preconditioner, initial residual
   double bb = 0.0, rz = 0.0, bad = 0.0;
   for (int f = C.tid; f < C.nf; f += kCtaThreads) {
@@ -336,20 +392,27 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
   // search's discontinuous decisions on the oracle's side
   while (ok && bb > 0.0) {
     for (; it < max_it; ++it) {
-      double pw = 0.0, z1 = 0.0, z2 = 0.0;
+      // three barriers per iteration: (1) inside the p.w reduction (also publishes w), (2) inside the
+      // {r.r, r.z} reduction, (3) after the update of p, which the next product gathers
+      long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+      if (tph) c0 = clock64();
+      double s1[1] = {0.0};
       if (C.regular) {
-        pw = cta_matvec_bcsr(C, C.p, C.w, C.pblk);
+        s1[0] = cta_matvec_bcsr<false>(C, C.p, C.w, C.pblk);
       } else {
         cta_matvec(C, C.p, C.w);
-        for (int i = C.tid; i < C.n; i += kCtaThreads) pw += C.p[i] * C.w[i];
+        for (int i = C.tid; i < C.n; i += kCtaThreads) s1[0] += C.p[i] * C.w[i];
       }
-      block_sum3(C, pw, z1, z2);
+      if (tph) c1 = clock64();
+      block_sum_db(C, s1, 0);
+      if (tph) c2 = clock64();
+      const double pw = s1[0];
       if (!(pw > 0.0) || !isfinite(pw)) {  // not positive definite in working precision
         ok = false;
         break;
       }
       const double alpha = rz / pw;
-      double rr = 0.0, rz_new = 0.0, z3 = 0.0;
+      double s2[2] = {0.0, 0.0};  // r.r, r.z
       for (int f = C.tid; f < C.nf; f += kCtaThreads) {  // one 16-byte access per vector and node
         const double2 pf = P2(C.p)[f], wf = P2(C.w)[f], yf = P2(C.y)[f], rf = P2(C.r)[f];
         const double y0 = yf.x + alpha * pf.x, y1 = yf.y + alpha * pf.y;
@@ -358,17 +421,26 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
         P2(C.r)[f] = make_double2(r0, r1);
         const double z0 = C.pinv[3 * f] * r0 + C.pinv[3 * f + 1] * r1, zz1 = C.pinv[3 * f + 1] * r0 + C.pinv[3 * f + 2] * r1;
         P2(C.z)[f] = make_double2(z0, zz1);
-        rr += r0 * r0 + r1 * r1;
-        rz_new += r0 * z0 + r1 * zz1;
+        s2[0] += r0 * r0 + r1 * r1;
+        s2[1] += r0 * z0 + r1 * zz1;
       }
-      block_sum3(C, rr, rz_new, z3);
+      if (tph) c3 = clock64();
+      block_sum_db(C, s2, 1);
+      if (tph) c4 = clock64();
+      if (tph) {
+        tph[0] += c1 - c0;  // product
+        tph[1] += c2 - c1;  // reduction 1
+        tph[2] += c3 - c2;  // vector update
+        tph[3] += c4 - c3;  // reduction 2
+      }
+      const double rr = s2[0], rz_new = s2[1];
       if (rr <= tol2) {
         ++it;
         break;
       }
       const double beta = rz_new / rz;
       rz = rz_new;
-      for (int f = C.tid; f < C.nf; f += kCtaThreads) {
+      for (int f = C.tid; f < C.nf; f += kCtaThreads) {  // same thread <-> node mapping as above: z[f] is this thread's own
         const double2 zf = P2(C.z)[f], pf = P2(C.p)[f];
         P2(C.p)[f] = make_double2(zf.x + beta * pf.x, zf.y + beta * pf.y);
       }
@@ -443,6 +515,7 @@ template <int MINB>
 __global__ void __launch_bounds__(kCtaThreads, MINB)
 solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const CtaComp* comps, unsigned smem_doubles) {
   __shared__ double red[3 * (kCtaThreads / 32)];
+  __shared__ double red2[4 * (kCtaThreads / 32)];
   const CtaComp cc = comps[blockIdx.x];
   CtaCtx C;
   C.tid = threadIdx.x;
@@ -483,6 +556,13 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
   C.twin = A.twin + cc.e_off;
   C.fdst = A.fdst + cc.e_off;
   C.regular = cc.regular != 0;
+#pragma unroll
+  for (int i = 0; i < kCtaRowsCached; ++i) {
+    const int l = (int)threadIdx.x + i * kCtaThreads;
+    C.row_f[i] = l < C.Nc ? C.freeof[l] : -1;
+    C.row_deg[i] = l < C.Nc ? C.outptr[l + 1] - C.outptr[l] : 0u;
+    C.row_slot[i] = l < C.Nc ? C.ell_base[l >> 5] + (uint32_t)(l & 31) : 0u;
+  }
   // CG vectors on chip while they fit in the launch's dynamic shared memory, in order of how often an
   // iteration touches them: p (randomly gathered by the matvec), w, r, z, y, then the preconditioner
   extern __shared__ __align__(16) double cg_smem[];
@@ -503,6 +583,7 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
     take(C.pinv, 3 * (size_t)C.nf);
   }
   C.red = red;
+  C.red2 = red2;
   const uint32_t c = cc.slot;
   const int tid = C.tid, lane = tid & 31;
   if (P.st_times && tid == 0) {
@@ -534,6 +615,10 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
     }
     return;
   }
+  const bool prof = P.st_cycles != nullptr;
+  long long t_begin = 0, t_lm = 0, t_eval = 0, t_mark = 0;
+  long long tph[4] = {0, 0, 0, 0};
+  if (prof) t_begin = clock64();
   double cost = cta_eval(C, C.x, K);
   double gmax = cta_assemble<false>(C, true, K);
   const double cost0 = cost;
@@ -572,8 +657,10 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
     ++iter;
     success = false;
     double model_change = 0.0, gd = 0.0, dmax = 0.0;
-    bool valid = cta_lm_step(C, radius, K, &model_change, &gd, &dmax, &cg_iters, P.st_cycles != nullptr, &worst_res,
-                             &n_maxit);
+    if (prof) t_mark = clock64();
+    bool valid = cta_lm_step(C, radius, K, &model_change, &gd, &dmax, &cg_iters, false, &worst_res, &n_maxit,
+                             prof ? tph : nullptr);
+    if (prof) t_lm += clock64() - t_mark;
     valid = valid && (model_change > 0.0);
     if (!valid) {
       if (++n_invalid >= K.max_invalid) { term = LFR_TERM_FAILURE; break; }
@@ -583,7 +670,9 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
     }
     n_invalid = 0;
     cta_candidate(C, 1.0, K);
+    if (prof) t_mark = clock64();
     double cost_c = cta_eval(C, C.xc, K);
+    if (prof) t_eval += clock64() - t_mark;
     bool c_valid = isfinite(cost_c);
     if (!c_valid || cost_c > cost + K.ls_suff * gd * 1.0) {
       LsSample initial{0.0, cost, gd, true, true};
@@ -663,12 +752,13 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
     P.st_ls[c] = ls_steps;
     if (P.st_cycles) {
       unsigned long long* o = P.st_cycles + 8 * (size_t)c;
-      o[0] = o[1] = o[2] = 0;
-      o[3] = n_maxit;
-      o[5] = (unsigned long long)__double_as_longlong(worst_res);
+      o[0] = (unsigned long long)(clock64() - t_begin);  // total, of which o[2] in the PCG solves
+      o[2] = (unsigned long long)t_lm;
+      o[3] = ((unsigned long long)(tph[0] >> 8) << 32) | (unsigned long long)min((long long)0xffffffffll, tph[1] >> 8);  // product | reduction 1, 256-cycle units
+      o[5] = ((unsigned long long)(tph[2] >> 8) << 32) | (unsigned long long)min((long long)0xffffffffll, tph[3] >> 8);  // update | reduction 2
       o[4] = cg_iters;
       o[1] = 1;  // marks a CTA-tier component
-      o[6] = (unsigned long long)ls_steps << 32;
+      o[6] = ((unsigned long long)ls_steps << 32) | (unsigned long long)min((long long)0xffffffffll, t_eval >> 10);  // + first-candidate evaluations, kcycles
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       o[7] = smid;
@@ -799,6 +889,7 @@ cta_prepare_kernel(const DevProblem P, const CtaArrays A, CtaComp* comps) {
     for (uint32_t sidx = sb; sidx < se; ++sidx) {
       uint32_t wmax = 0;
       for (uint32_t l = 32 * sidx; l < min(Nc, 32 * sidx + 32); ++l) wmax = max(wmax, outptr[l + 1] - outptr[l]);
+      wmax = (wmax + 3u) & ~3u;  // rows are walked in groups of four slots
       ell_base[sidx + 1] = 32 * wmax;
       mine += 32 * wmax;
     }
@@ -810,6 +901,16 @@ cta_prepare_kernel(const DevProblem P, const CtaArrays A, CtaComp* comps) {
     }
   }
   __syncthreads();
+  {  // every slot starts as "zero block, no column": real blocks are written by the assembly each iteration
+    double2* bE01 = const_cast<double2*>(A.bE01) + cc.ell_off;
+    double2* bE23 = const_cast<double2*>(A.bE23) + cc.ell_off;
+    const uint32_t n_slots = ell_base[(Nc + 31) / 32];
+    for (uint32_t i = tid; i < n_slots; i += kCtaThreads) {
+      fdstE[i] = -1;
+      bE01[i] = make_double2(0.0, 0.0);
+      bE23[i] = make_double2(0.0, 0.0);
+    }
+  }
   // kept-edge records in CSR order + in-degree counts
   for (uint32_t l = wid; l < Nc; l += kWarps) {
     const uint32_t v = node[l], rs = P.row_ptr[v], re = P.row_ptr[v + 1];

@@ -19,7 +19,9 @@ import torch  # noqa: E402
 
 s = torch.cuda.current_stream().cuda_stream
 for st in settings:
-    os.environ["LFR_CTA_MINB"] = st
+    mb, _, sv = st.partition("/")
+    os.environ["LFR_CTA_MINB"] = mb
+    os.environ["LFR_CTA_SMEM_VECS"] = sv or "6,6,6,6"
     plan = Plan(lib, p)
     ts = []
     for i in range(5):

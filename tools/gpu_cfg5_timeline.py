@@ -31,6 +31,8 @@ for i in range(n_solves):
     plan.solve(s)
     e1.record()
     torch.cuda.synchronize()
+    _, stt = plan.download(s)
+    p_iters = stt["iterations"].astype(np.float64)
     cyc = np.zeros((Cn, 8), dtype=np.uint64)
     tm = np.zeros((Cn, 2), dtype=np.uint64)
     assert fc(plan.handle, cyc.ctypes.data) == 0 and ft(plan.handle, tm.ctypes.data) == 0
@@ -47,6 +49,22 @@ for i in range(n_solves):
         print("   CTA tier: sum of durations %.0f ms over %d SMs -> /296 = %.1f ms;  start p50 %.1f p90 %.1f max %.1f;  duration p50 %.2f p99 %.1f max %.1f" % (
             dur[cta].sum(), len(np.unique(sm)), dur[cta].sum() / 296.0, np.median(st[cta]), np.percentile(st[cta], 90), st[cta].max(),
             np.median(dur[cta]), np.percentile(dur[cta], 99), dur[cta].max()))
+        tot = cyc[cta, 0].astype(np.float64); lm = cyc[cta, 2].astype(np.float64); ev = (cyc[cta, 6] & np.uint64(0xffffffff)).astype(np.float64) * 1024
+        cg = cyc[cta, 4].astype(np.float64); its = np.maximum(1, p_iters[cta])
+        print("   CTA tier cycles: total %.3g  PCG %.1f%%  first-candidate eval %.1f%%;  cycles per CG iteration p50 %.0f p90 %.0f;  CG iterations per LM step p50 %.0f p90 %.0f" % (
+            tot.sum(), 100 * lm.sum() / tot.sum(), 100 * ev.sum() / tot.sum(), np.median(lm / np.maximum(cg, 1)), np.percentile(lm / np.maximum(cg, 1), 90),
+            np.median(cg / its), np.percentile(cg / its, 90)))
+        mv = (cyc[cta, 3] >> np.uint64(32)).astype(np.float64) * 256; r1 = (cyc[cta, 3] & np.uint64(0xffffffff)).astype(np.float64) * 256
+        up = (cyc[cta, 5] >> np.uint64(32)).astype(np.float64) * 256; r2 = (cyc[cta, 5] & np.uint64(0xffffffff)).astype(np.float64) * 256
+        print("   PCG split (thread 0's clock): product %.1f%%  reduction1 %.1f%%  update %.1f%%  reduction2 %.1f%%  rest %.1f%%" % tuple(
+            100 * x / lm.sum() for x in (mv.sum(), r1.sum(), up.sum(), r2.sum(), lm.sum() - mv.sum() - r1.sum() - up.sum() - r2.sum())))
+        for lo, hi in ((49, 100), (101, 250), (251, 504), (505, 1000)):
+            m = (sizes[cta] >= lo) & (sizes[cta] <= hi)
+            print("      nodes %4d-%4d per CG iteration: product %.0f  red1 %.0f  update %.0f  red2 %.0f" % (lo, hi, np.median((mv / np.maximum(cg, 1))[m]),
+                  np.median((r1 / np.maximum(cg, 1))[m]), np.median((up / np.maximum(cg, 1))[m]), np.median((r2 / np.maximum(cg, 1))[m])))
+            if m.any():
+                print("      nodes %4d-%4d: n %5d  cycles/CG-iteration p50 %.0f  CG its/LM step p50 %.0f  LM its p50 %.0f  duration p50 %.2f ms" % (
+                    lo, hi, int(m.sum()), np.median((lm / np.maximum(cg, 1))[m]), np.median((cg / its)[m]), np.median(its[m]), np.median(dur[cta][m])))
         idx = np.where(cta)[0]
         order = idx[np.argsort(-en[idx])[:5]]
         for k in order:
