@@ -680,9 +680,9 @@ int set_kernel_attrs() {
   int dev = 0;
   LFR_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 16 && done_for_device[dev]) return LFR_OK;
-  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  LFR_CUDA(cudaFuncSetAttribute(lfr::solve_cta_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kMaxSmemPerBlock));
   LFR_CUDA(cudaFuncSetAttribute(lfr::solve_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -741,12 +741,13 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
       const size_t cg_bytes = std::min<size_t>(200 * 1024, (size_t)g.max_free * per_node * sizeof(double));
       const lfr::CtaComp* comps = pl->L_comps.as<lfr::CtaComp>() + g.first;
       const unsigned smem_doubles = (unsigned)(cg_bytes / sizeof(double));
+      // (512-thread CTAs were measured too — profiles/r02_cta_tier_tuning.txt: slower at every size class)
       if (g.minb >= 4)
-        lfr::solve_cta_kernel<4><<<g.n, lfr::kCtaThreads, cg_bytes, bs>>>(P_hbm, pl->K, A, comps, smem_doubles);
+        lfr::solve_cta_kernel<256, 4><<<g.n, 256, cg_bytes, bs>>>(P_hbm, pl->K, A, comps, smem_doubles);
       else if (g.minb == 3)
-        lfr::solve_cta_kernel<3><<<g.n, lfr::kCtaThreads, cg_bytes, bs>>>(P_hbm, pl->K, A, comps, smem_doubles);
+        lfr::solve_cta_kernel<256, 3><<<g.n, 256, cg_bytes, bs>>>(P_hbm, pl->K, A, comps, smem_doubles);
       else
-        lfr::solve_cta_kernel<2><<<g.n, lfr::kCtaThreads, cg_bytes, bs>>>(P_hbm, pl->K, A, comps, smem_doubles);
+        lfr::solve_cta_kernel<256, 2><<<g.n, 256, cg_bytes, bs>>>(P_hbm, pl->K, A, comps, smem_doubles);
       LFR_CUDA(cudaGetLastError());
     }
   }

@@ -55,14 +55,15 @@ struct CtaArrays {
   uint64_t total_free;     // sum of nf over all large components (stride between vectors)
 };
 
-constexpr int kCtaThreads = 256;
+constexpr int kCtaThreads = 256;     // preparation kernel; smallest solve variant
+constexpr int kCtaMaxThreads = 512;  // largest solve variant (CtaCtx::nt)
 enum { V_G = 0, V_S, V_DL, V_D2, V_R, V_Z, V_P, V_W, V_Y, V_COUNT };  // 2-doubles-per-node vectors
 // then three 3-doubles-per-node arrays: diagonal blocks (d00, d01, d11), their damped scaled form, its inverse
 
 constexpr int kCtaRowsCached = 4;  // covers components up to 1024 nodes (solve.cc:586 caps them at #images)
 
 struct CtaCtx {
-  int tid, Nc, Ec, nf, n;
+  int tid, nt, Nc, Ec, nf, n;  // nt = threads of this CTA (256 or 512: compile-time in every instantiation)
   const uint32_t *meta, *inlist, *node, *outptr, *inptr, *lof;
   const int32_t* freeof;
   double *scr, *q, *x, *xc, *g, *S, *dl, *D2, *r, *z, *p, *w, *y, *diag, *pinv, *pblk;
@@ -88,7 +89,7 @@ __device__ __forceinline__ void block_sum3(const CtaCtx& C, double& a, double& b
     b += __shfl_xor_sync(kFull, b, o);
     c += __shfl_xor_sync(kFull, c, o);
   }
-  const int w = C.tid >> 5, nw = kCtaThreads / 32;
+  const int w = C.tid >> 5, nw = C.nt >> 5;
   __syncthreads();  // previous users of `red` are done
   if ((C.tid & 31) == 0) {
     C.red[w] = a;
@@ -115,7 +116,7 @@ __device__ __forceinline__ void block_sum_db(const CtaCtx& C, double (&v)[N], in
 #pragma unroll
     for (int k = 0; k < N; ++k) v[k] += __shfl_xor_sync(kFull, v[k], o);
   }
-  constexpr int nw = kCtaThreads / 32;
+  const int nw = C.nt >> 5;
   double* line = C.red2 + parity * 2 * nw;
   if ((C.tid & 31) == 0) {
 #pragma unroll
@@ -134,7 +135,7 @@ __device__ __forceinline__ void block_sum_db(const CtaCtx& C, double (&v)[N], in
 __device__ __forceinline__ double block_max(const CtaCtx& C, double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
-  const int w = C.tid >> 5, nw = kCtaThreads / 32;
+  const int w = C.tid >> 5, nw = C.nt >> 5;
   __syncthreads();
   if ((C.tid & 31) == 0) C.red[w] = v;
   __syncthreads();
@@ -147,7 +148,7 @@ __device__ __forceinline__ double block_max(const CtaCtx& C, double v) {
 __device__ __forceinline__ double cta_eval(const CtaCtx& C, const double* xe, const DevConsts& K) {
   double cost = 0.0, z1 = 0.0, z2 = 0.0;
   const int E = C.Ec;
-  for (int j = C.tid; j < E; j += kCtaThreads) {
+  for (int j = C.tid; j < E; j += C.nt) {
     const uint32_t mt = C.meta[j];
     const int s = mt & 0x3fff, d = (mt >> 14) & 0x3fff, kind = mt >> 28;
     const float4* qp = C.rec + 5 * (size_t)j;
@@ -174,7 +175,7 @@ template <bool GRAD_ONLY>
 __device__ __forceinline__ double cta_assemble(const CtaCtx& C, bool first, const DevConsts& K) {
   const size_t E = C.Ec;
   double acc = 0.0, gmax = 0.0;
-  for (int f = C.tid; f < C.nf; f += kCtaThreads) {
+  for (int f = C.tid; f < C.nf; f += C.nt) {
     const int l = C.lof[f];
     double d00 = 0., d01 = 0., d11 = 0., g0 = 0., g1 = 0.;
     for (uint32_t j = C.outptr[l]; j < C.outptr[l + 1]; ++j) {
@@ -223,7 +224,7 @@ __device__ __forceinline__ double cta_assemble(const CtaCtx& C, bool first, cons
   gmax = block_max(C, gmax);  // (also makes S visible to every thread)
   if (C.regular) {
     // block-CSR form of S H S: one scaled 2x2 block per out-edge, edge + twin combined
-    for (int j = C.tid; j < C.Ec; j += kCtaThreads) {
+    for (int j = C.tid; j < C.Ec; j += C.nt) {
       const uint32_t mt = C.meta[j];
       const int fs = C.freeof[mt & 0x3fff], fd = C.fdst[j];
       if (fs < 0 || fd < 0) continue;
@@ -247,7 +248,7 @@ __device__ __forceinline__ double cta_assemble(const CtaCtx& C, bool first, cons
 __device__ __forceinline__ void cta_matvec(const CtaCtx& C, const double* v, double* w) {
   const size_t E = C.Ec;
 #pragma unroll 4
-  for (int j = C.tid; j < C.Ec; j += kCtaThreads) {
+  for (int j = C.tid; j < C.Ec; j += C.nt) {
     const uint32_t mt = C.meta[j];
     const int fs = C.freeof[mt & 0x3fff], fd = C.freeof[(mt >> 14) & 0x3fff];
     double s0 = 0., s1 = 0., t0 = 0., t1 = 0.;
@@ -265,7 +266,7 @@ __device__ __forceinline__ void cta_matvec(const CtaCtx& C, const double* v, dou
     C.q[2 * (size_t)j + 1] = a * (t1 - (m10 * s0 + m11 * s1));
   }
   __syncthreads();
-  for (int f = C.tid; f < C.nf; f += kCtaThreads) {
+  for (int f = C.tid; f < C.nf; f += C.nt) {
     const int l = C.lof[f];
     double a0 = 0., a1 = 0.;
 #pragma unroll 4
@@ -334,7 +335,7 @@ __device__ __forceinline__ double cta_matvec_bcsr(const CtaCtx& C, const double*
 #pragma unroll
   for (int i = 0; i < kCtaRowsCached; ++i)
     if (C.row_f[i] >= 0) dot += cta_block_row(C, v2, w2, pblk, C.row_f[i], C.row_deg[i], C.row_slot[i]);
-  for (int l = C.tid + kCtaRowsCached * kCtaThreads; l < C.Nc; l += kCtaThreads) {
+  for (int l = C.tid + kCtaRowsCached * C.nt; l < C.Nc; l += C.nt) {
     const int f = C.freeof[l];
     if (f < 0) continue;
     dot += cta_block_row(C, v2, w2, pblk, f, C.outptr[l + 1] - C.outptr[l],
@@ -351,7 +352,7 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
                                             double* worst_res, unsigned* n_maxit, long long* tph = nullptr) {
   // damping, preconditioner, initial residual
   double bb = 0.0, rz = 0.0, bad = 0.0;
-  for (int f = C.tid; f < C.nf; f += kCtaThreads) {
+  for (int f = C.tid; f < C.nf; f += C.nt) {
     const double s0 = C.S[2 * f], s1 = C.S[2 * f + 1];
     const double h00 = C.diag[3 * f] * s0 * s0, h01 = C.diag[3 * f + 1] * s0 * s1, h11 = C.diag[3 * f + 2] * s1 * s1;
     const double e0 = fmin(fmax(h00, K.min_diag), K.max_diag) / radius;
@@ -401,7 +402,7 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
         s1[0] = cta_matvec_bcsr<false>(C, C.p, C.w, C.pblk);
       } else {
         cta_matvec(C, C.p, C.w);
-        for (int i = C.tid; i < C.n; i += kCtaThreads) s1[0] += C.p[i] * C.w[i];
+        for (int i = C.tid; i < C.n; i += C.nt) s1[0] += C.p[i] * C.w[i];
       }
       if (tph) c1 = clock64();
       block_sum_db(C, s1, 0);
@@ -413,7 +414,7 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
       }
       const double alpha = rz / pw;
       double s2[2] = {0.0, 0.0};  // r.r, r.z
-      for (int f = C.tid; f < C.nf; f += kCtaThreads) {  // one 16-byte access per vector and node
+      for (int f = C.tid; f < C.nf; f += C.nt) {  // one 16-byte access per vector and node
         const double2 pf = P2(C.p)[f], wf = P2(C.w)[f], yf = P2(C.y)[f], rf = P2(C.r)[f];
         const double y0 = yf.x + alpha * pf.x, y1 = yf.y + alpha * pf.y;
         const double r0 = rf.x - alpha * wf.x, r1 = rf.y - alpha * wf.y;
@@ -440,7 +441,7 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
       }
       const double beta = rz_new / rz;
       rz = rz_new;
-      for (int f = C.tid; f < C.nf; f += kCtaThreads) {  // same thread <-> node mapping as above: z[f] is this thread's own
+      for (int f = C.tid; f < C.nf; f += C.nt) {  // same thread <-> node mapping as above: z[f] is this thread's own
         const double2 zf = P2(C.z)[f], pf = P2(C.p)[f];
         P2(C.p)[f] = make_double2(zf.x + beta * pf.x, zf.y + beta * pf.y);
       }
@@ -450,7 +451,7 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
     // true residual r = S g - A y, z = M^-1 r, p = z
     if (C.regular) cta_matvec_bcsr(C, C.y, C.w, C.pblk); else cta_matvec(C, C.y, C.w);
     double rt = 0.0, rzt = 0.0, z3 = 0.0;
-    for (int f = C.tid; f < C.nf; f += kCtaThreads) {
+    for (int f = C.tid; f < C.nf; f += C.nt) {
       const double r0 = C.S[2 * f] * C.g[2 * f] - C.w[2 * f], r1 = C.S[2 * f + 1] * C.g[2 * f + 1] - C.w[2 * f + 1];
       const double z0 = C.pinv[3 * f] * r0 + C.pinv[3 * f + 1] * r1, z1 = C.pinv[3 * f + 1] * r0 + C.pinv[3 * f + 2] * r1;
       C.r[2 * f] = r0;
@@ -472,7 +473,7 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
     if (it >= max_it) ++*n_maxit;
     if (C.regular) cta_matvec_bcsr(C, C.y, C.w, C.pblk); else cta_matvec(C, C.y, C.w);
     double e2 = 0.0, z1 = 0.0, z2 = 0.0;
-    for (int i = C.tid; i < C.n; i += kCtaThreads) {
+    for (int i = C.tid; i < C.n; i += C.nt) {
       const double d = C.S[i] * C.g[i] - C.w[i];
       e2 += d * d;
     }
@@ -480,7 +481,7 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
     *worst_res = fmax(*worst_res, sqrt(e2 / bb));
   }
   double mc = 0.0, dot = 0.0, nonfinite = 0.0, mx = 0.0;
-  for (int i = C.tid; i < C.n; i += kCtaThreads) {
+  for (int i = C.tid; i < C.n; i += C.nt) {
     const double y = C.y[i], si = C.S[i], gi = C.g[i];
     const double d = -si * y;
     C.dl[i] = d;
@@ -498,7 +499,7 @@ __device__ __forceinline__ bool cta_lm_step(const CtaCtx& C, double radius, cons
 }
 
 __device__ __forceinline__ void cta_candidate(const CtaCtx& C, double alpha, const DevConsts& K) {
-  for (int i = C.tid; i < 2 * C.Nc; i += kCtaThreads) {
+  for (int i = C.tid; i < 2 * C.Nc; i += C.nt) {
     const int f = C.freeof[i >> 1];
     double v = C.x[i];
     if (f >= 0) v = fmin(fmax(v + alpha * C.dl[2 * f + (i & 1)], -K.bound), K.bound);
@@ -511,14 +512,16 @@ __device__ __forceinline__ void cta_candidate(const CtaCtx& C, double alpha, con
 // ptxas: 128 registers at MINB = 2 spill no more than 255 do, profiles/): the CG loop is a chain of
 // block reductions, so an SM needs several resident CTAs to stay busy.  The host picks MINB and the
 // dynamic shared memory per size class of components.
-template <int MINB>
-__global__ void __launch_bounds__(kCtaThreads, MINB)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const CtaComp* comps, unsigned smem_doubles) {
-  __shared__ double red[3 * (kCtaThreads / 32)];
-  __shared__ double red2[4 * (kCtaThreads / 32)];
+  static_assert(NT == kCtaThreads || NT == kCtaMaxThreads, "reduction lines are sized for 8 or 16 warps");
+  __shared__ double red[3 * (NT / 32)];
+  __shared__ double red2[4 * (NT / 32)];
   const CtaComp cc = comps[blockIdx.x];
   CtaCtx C;
   C.tid = threadIdx.x;
+  C.nt = NT;
   C.Nc = (int)cc.Nc;
   C.Ec = (int)cc.Ec;
   C.nf = (int)cc.nf;
@@ -558,7 +561,7 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
   C.regular = cc.regular != 0;
 #pragma unroll
   for (int i = 0; i < kCtaRowsCached; ++i) {
-    const int l = (int)threadIdx.x + i * kCtaThreads;
+    const int l = (int)threadIdx.x + i * NT;
     C.row_f[i] = l < C.Nc ? C.freeof[l] : -1;
     C.row_deg[i] = l < C.Nc ? C.outptr[l + 1] - C.outptr[l] : 0u;
     C.row_slot[i] = l < C.Nc ? C.ell_base[l >> 5] + (uint32_t)(l & 31) : 0u;
@@ -593,7 +596,7 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
   }
 
   // start point: IterationZero projects the free blocks onto the box
-  for (int l = tid; l < C.Nc; l += kCtaThreads) {
+  for (int l = tid; l < C.Nc; l += C.nt) {
     const uint32_t v = C.node[l];
     double p0 = P.positions[2 * (size_t)v], p1 = P.positions[2 * (size_t)v + 1];
     if (C.freeof[l] >= 0) {
@@ -629,7 +632,7 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
   bool success = true;
   auto norms = [&](double* xn2, double* dn2) {
     double a = 0.0, b = 0.0, z = 0.0;
-    for (int i = tid; i < C.n; i += kCtaThreads) {
+    for (int i = tid; i < C.n; i += C.nt) {
       const int l = C.lof[i >> 1];
       const double xv = C.x[2 * l + (i & 1)], dv = xv - C.xc[2 * l + (i & 1)];
       a += xv * xv;
@@ -642,7 +645,7 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
   double x_norm;
   {
     double a = 0.0, b = 0.0, z = 0.0;
-    for (int i = tid; i < C.n; i += kCtaThreads) {
+    for (int i = tid; i < C.n; i += C.nt) {
       const int l = C.lof[i >> 1];
       const double xv = C.x[2 * l + (i & 1)];
       a += xv * xv;
@@ -702,7 +705,7 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
         if (c_valid && !(cost_c > cost + K.ls_suff * gd * step)) { ls_ok = true; break; }
       }
       if (ls_ok) {
-        for (int i = tid; i < C.n; i += kCtaThreads) C.dl[i] *= current.x;
+        for (int i = tid; i < C.n; i += C.nt) C.dl[i] *= current.x;
         __syncthreads();
       } else {
         cta_candidate(C, 1.0, K);
@@ -719,7 +722,7 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
     const double rho = (cost - cost_c) / model_change;
     if (rho > K.min_rel_decrease) {
       double a2 = 0.0, z1 = 0.0, z2 = 0.0;
-      for (int i = tid; i < 2 * C.Nc; i += kCtaThreads) {
+      for (int i = tid; i < 2 * C.Nc; i += C.nt) {
         const double v = C.xc[i];
         C.x[i] = v;
         if (C.freeof[i >> 1] >= 0) a2 += v * v;
@@ -739,7 +742,7 @@ solve_cta_kernel(const DevProblem P, const DevConsts K, const CtaArrays A, const
   }
   // (not after FAILURE: Ceres only commits a usable solution, solver.cc Minimize / IsSolutionUsable)
   if (term != LFR_TERM_FAILURE) {
-    for (int i = tid; i < C.n; i += kCtaThreads) {
+    for (int i = tid; i < C.n; i += C.nt) {
       const int l = C.lof[i >> 1];
       P.positions_out[2 * (size_t)C.node[l] + (i & 1)] = C.x[2 * l + (i & 1)];
     }

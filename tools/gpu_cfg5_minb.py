@@ -19,9 +19,10 @@ import torch  # noqa: E402
 
 s = torch.cuda.current_stream().cuda_stream
 for st in settings:
-    mb, _, sv = st.partition("/")
-    os.environ["LFR_CTA_MINB"] = mb
-    os.environ["LFR_CTA_SMEM_VECS"] = sv or "6,6,6,6"
+    parts = (st.split("/") + ["", ""])[:3]
+    os.environ["LFR_CTA_MINB"] = parts[0]
+    os.environ["LFR_CTA_SMEM_VECS"] = parts[1] or "6,6,6,6"
+    os.environ["LFR_CTA_NT"] = parts[2] or "256,256,256,256"
     plan = Plan(lib, p)
     ts = []
     for i in range(5):
