@@ -128,6 +128,7 @@ struct Bucket {
   uint32_t offset = 0;  // into the bucket-list buffer
   uint32_t n = 0;
   int emax = 0, ncmax = 0, n2max = 0, smem_per_warp = 0, warps = 4;
+  uint64_t scratch_offset = 0;  // tile tier: first double of this launch's global scratch (12 * emax per CTA)
   int variant = 0;  // 0: shared-memory Cholesky kernel (n <= 64); 16 / 32: register Gauss-Jordan kernel (n <= variant)
   bool stages_edges() const { return variant != 0; }  // warp2 / tile tiers pull their edge records into shared memory
 };
@@ -154,7 +155,7 @@ struct lfr_plan {
   uint32_t N = 0, C = 0;
   uint64_t E = 0;
   uint32_t total_slots = 0;
-  DevBuf row_ptr, edges, track, comp, is_root, comp_ptr, comp_nodes, local_of, pos, pos_init, stats, cycles, times, lists;
+  DevBuf row_ptr, edges, track, comp, is_root, comp_ptr, comp_nodes, local_of, pos, pos_init, stats, cycles, times, lists, tile_scratch;
   // `stats` is one block (one memset, one D2H copy): cost0[Cp] cost1[Cp] iter[Cp] term[Cp] ls[Cp] kept[Cp] err[2] pull[2 x u64]
   uint32_t Cp = 0;               // C rounded up to an even count
   bool pos_is_staged = false;    // lfr_solve(): the start point was uploaded straight into `pos`
@@ -262,7 +263,7 @@ namespace {
 void free_plan(lfr_plan* pl) {
   if (!pl) return;
   DevBuf* bufs[] = {&pl->row_ptr, &pl->edges, &pl->track, &pl->comp, &pl->is_root, &pl->comp_ptr, &pl->comp_nodes,
-                    &pl->local_of, &pl->pos, &pl->pos_init, &pl->stats, &pl->cycles, &pl->times, &pl->lists, &pl->L_comps, &pl->L_rec, &pl->L_meta,
+                    &pl->local_of, &pl->pos, &pl->pos_init, &pl->stats, &pl->cycles, &pl->times, &pl->lists, &pl->tile_scratch, &pl->L_comps, &pl->L_rec, &pl->L_meta,
                     &pl->L_inlist, &pl->L_twin, &pl->L_fdst, &pl->L_bE01, &pl->L_bE23, &pl->L_fdstE, &pl->L_ell_base, &pl->L_scr, &pl->L_q, &pl->L_node, &pl->L_outptr, &pl->L_inptr, &pl->L_freeof,
                     &pl->L_x, &pl->L_xc, &pl->L_lof, &pl->L_vec};
   for (DevBuf* b : bufs) b->release();
@@ -290,6 +291,8 @@ int upload(DevBuf* d, const T* h, size_t count, cudaStream_t s) {
 // components do not dictate the carve-up of everyone else.  Buckets are
 // launched on concurrent streams, largest components first.
 int build_buckets(lfr_plan* pl, const lfr_problem* p) {
+  // shared-memory classes of a launch (finer classes — one per "one more CTA fits an SM" boundary — were
+  // measured on cfg4: 26 launches instead of 15, same solve time; profiles/r02_tile_tier_occupancy.txt)
   static const int kClass[] = {2048, 3072, 4096, 6144, 8192, 12288, 16384, 24576, 32768, 57344, kMaxSmemPerBlock};
   constexpr int n_class = sizeof(kClass) / sizeof(kClass[0]);
   // register warp kernel (8..32), register tile kernel (132 = 64 threads x NREG 32; 48, 64: 64 threads;
@@ -626,6 +629,15 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
   host_mark(0);
   LFR_TRY(build_buckets(pl, p));  // host work overlaps the copies above
   host_mark(1);
+  {
+    uint64_t scratch = 0;
+    for (Bucket& b : pl->buckets)
+      if (LFR_TILE_SCRATCH_GLOBAL && (b.variant >= 48 || b.variant == 132)) {
+        b.scratch_offset = scratch;
+        scratch += 12ull * (uint64_t)b.emax * b.n;
+      }
+    if (scratch) LFR_TRY(pl->tile_scratch.reserve(sizeof(double) * scratch));
+  }
   if (zc_edges && pl->needs_hbm_edges) {
     // mixed schedule: the Cholesky-warp tier reads edge records from global memory by index, so the
     // array goes to HBM after all — on its own stream, and only that tier waits for it
@@ -766,6 +778,7 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
     wb.ncmax = b.ncmax;
     wb.n2max = b.n2max;
     wb.smem_per_warp = b.smem_per_warp;
+    wb.scratch = (LFR_TILE_SCRATCH_GLOBAL && (b.variant >= 48 || b.variant == 132)) ? pl->tile_scratch.as<double>() + b.scratch_offset : nullptr;
     const size_t smem = (size_t)b.smem_per_warp * b.warps;
     const unsigned grid = (b.n + b.warps - 1) / b.warps;
     const lfr::DevProblem& P = b.stages_edges() ? P_stage : P_hbm;
@@ -1088,6 +1101,12 @@ int lfr_debug_time_schedule(const lfr_problem* p, const lfr_options* opt, int re
       b2 = std::min(b2, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
     }
     std::fprintf(stderr, "node loop alone %.1f us (sink %llu)\n", b2, (unsigned long long)sink);
+  }
+  if (std::getenv("LFR_SCHED_DUMP")) {
+    for (const Bucket& b : pl.buckets)
+      std::fprintf(stderr, "bucket variant %3d  n %6u  emax %5d ncmax %4d n2max %3d  smem/warp %6d  warps %d  -> CTAs/SM by smem %d\n", b.variant,
+                   b.n, b.emax, b.ncmax, b.n2max, b.smem_per_warp, b.warps, (int)(kMaxSmemPerBlock / (b.smem_per_warp * b.warps + 1024)));
+    std::fprintf(stderr, "CTA tier: %zu components\n", pl.large_slots.size());
   }
   *best_us = best;
   if (n_launches) *n_launches = (int)pl.buckets.size() + (pl.large_slots.empty() ? 0 : 1);  // (CTA tier counted once here)

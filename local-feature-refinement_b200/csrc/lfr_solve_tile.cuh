@@ -11,6 +11,13 @@
 
 namespace lfr {
 
+// 1: the per-edge evaluation / assembly scratch (96 of 186 bytes per candidate edge) lives in a per-CTA
+// global area instead of shared memory.  Measured on cfg4 (profiles/r02_tile_tier_occupancy.txt): 1.4x
+// the resident components, each 1.3x slower (scratch latency) -> same solve time; left off.
+#ifndef LFR_TILE_SCRATCH_GLOBAL
+#define LFR_TILE_SCRATCH_GLOBAL 0
+#endif
+
 struct TileLayout {
   int stage, bar;
   int x, xc, g, S, dl, H, scr, tup, prow, red, hdr;
@@ -28,8 +35,16 @@ struct TileLayout {
     S = o; o += 8 * n2max;
     dl = o; o += 8 * n2max;
     H = o; o += 8 * n2max * ldh;
+    // scr (7 doubles per candidate edge: the staged evaluation) and tup (5: the assembly tuples) live
+    // in a per-CTA global scratch area (WarpBucket::scratch), not here: at 96 of 186 bytes per edge they
+    // were what held this tier to 1-2 CTAs (2-4 warps) per SM on ETH3D-scale scenes
+#if LFR_TILE_SCRATCH_GLOBAL
+    scr = 0;
+    tup = 0;
+#else
     scr = o; o += 8 * 7 * emax;
     tup = o; o += 8 * 5 * emax;
+#endif
     o = align_up(o, 16);
     prow = o; o += 8 * 4 * 84;   // double-buffered pair of pivot rows: 2 x 2 x (80 columns, rhs, spare)
     red = o; o += 8 * 3 * 4;     // block reductions (<= 4 warps)
@@ -372,8 +387,13 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
   C.S = (double*)(base + L.S);
   C.dl = (double*)(base + L.dl);
   C.H = (double*)(base + L.H);
+#if LFR_TILE_SCRATCH_GLOBAL
+  C.scr = B.scratch + (size_t)blockIdx.x * 12 * (size_t)B.emax;  // global (L1/L2-resident): lanes <-> edges, SoA
+  C.tup = C.scr + 7 * (size_t)B.emax;
+#else
   C.scr = (double*)(base + L.scr);
   C.tup = (double*)(base + L.tup);
+#endif
   C.prow = (double*)(base + L.prow);
   C.red = (double*)(base + L.red);
   int* hdr = (int*)(base + L.hdr);
@@ -392,6 +412,13 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
 
   const int Nc = (int)(P.comp_ptr[c + 1] - P.comp_ptr[c]);
   C.Nc = Nc;
+  long long t_begin = 0, t_lm = 0, t_mark = 0;
+  if (P.st_cycles) t_begin = clock64();
+  if (P.st_times && tid == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    P.st_times[2 * (size_t)c] = ns;
+  }
   // ---- setup by warp 0 (solve.cc:98-143), shared with the warp kernel -----------------------
   if (tid < 32) {
     int Ec = 0, nf = 0;
@@ -445,7 +472,9 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     ++iter;
     success = false;
     double model_change = 0.0, gd = 0.0, dmax = 0.0;
+    if (P.st_cycles) t_mark = clock64();
     bool valid = tile_lm_step<T, NREG>(C, radius, K, &model_change, &gd, &dmax);
+    if (P.st_cycles) t_lm += clock64() - t_mark;
     valid = valid && (model_change > 0.0);
     if (!valid) {
       if (++n_invalid >= K.max_invalid) { term = LFR_TERM_FAILURE; break; }
@@ -542,9 +571,19 @@ solve_tile_kernel(const DevProblem P, const DevConsts K, const WarpBucket B) {
     P.st_ls[c] = ls_steps;
     if (P.st_cycles) {
       unsigned long long* o = P.st_cycles + 8 * (size_t)c;
-      o[0] = o[2] = o[3] = o[4] = o[5] = o[7] = 0;
+      o[2] = o[3] = o[5] = 0;
+      o[0] = (unsigned long long)(clock64() - t_begin);
+      o[4] = (unsigned long long)t_lm;  // of which in the linear solves
       o[1] = 2;  // marks a tile-tier component
       o[6] = (unsigned long long)ls_steps << 32;
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      o[7] = smid;
+    }
+    if (P.st_times) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      P.st_times[2 * (size_t)c + 1] = ns;
     }
   }
 }

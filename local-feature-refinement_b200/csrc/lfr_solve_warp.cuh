@@ -57,6 +57,7 @@ struct WarpBucket {
   int ncmax;   // max nodes
   int n2max;   // max unknowns (2 x free nodes)
   int smem_per_warp;
+  double* scratch;  // tile tier: 12 doubles per candidate edge and CTA (12 * emax * gridDim.x), else unused
 };
 
 __host__ __device__ inline int tri(int n) { return n * (n + 1) / 2; }
