@@ -55,6 +55,7 @@ constexpr int kMaxSmemPerBlock = 227 * 1024;
 // Components with more unknowns than this (and <= 32) take the two-warp tile kernel <64, 32> instead of
 // the one-warp register kernel; 32 = never.  Overridden per plan by LFR_TILE_FROM_N.
 constexpr int kTileFromDefault = 32;
+constexpr int kScheduleThreadsMax = 8;  // host threads that classify the dispatch list (build_buckets)
 constexpr int kMaxStreams = 12;
 
 lfr::DevConsts make_consts(const lfr_options& o) {
@@ -326,8 +327,6 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   pl->large_cand.clear();
   pl->large_free.clear();
   pl->large_ell.clear();
-  Bucket caps[kKeys];
-  uint32_t count[kKeys] = {};
   const uint32_t* comp_ptr = p->comp_ptr;
   const uint32_t* comp_nodes = p->comp_nodes;
   const uint32_t* row_ptr = p->row_ptr;
@@ -336,71 +335,131 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   const uint32_t n_nodes = p->n_nodes;
   uint16_t* key_of = pl->sched_key.data();
   lfr_plan::SchedDim* dim = pl->sched_dim.data();
-  for (uint32_t c = 0; c < C; ++c) {
-    const uint32_t beg = comp_ptr[c], end = comp_ptr[c + 1];
-    if (end < beg || end > pl->total_slots) return fail(LFR_EINVAL, "comp_ptr not monotone");
-    const uint32_t nc = end - beg;
-    pl->comp_size[c] = nc;
-    key_of[c] = kNoKey;
-    if (nc <= 1) continue;  // solve.cc:619-622
-    if (owner && owner[c] != pl->owner_id) continue;  // another device's component
-    ++pl->n_solved;
-    uint64_t eup = 0;
-    uint32_t nfree = 0;
-    for (uint32_t i = beg; i < end; ++i) {
-      const uint32_t v = comp_nodes[i];
-      if (v >= n_nodes) return fail(LFR_EINVAL, "comp_nodes out of range");
-      const uint32_t r0 = row_ptr[v], r1 = row_ptr[v + 1];
-      if (r1 < r0) return fail(LFR_EINVAL, "row_ptr not monotone");
-      eup += r1 - r0;
-      nfree += is_root[v] ? 0 : 1;
-    }
-    const int n2 = std::max(2 * (int)nfree, 2);
-    auto to_cta_tier = [&]() -> int {
-      if (nc > 16383) return fail(LFR_EUNSUPPORTED, "component with more than 16383 nodes");
-      pl->large_slots.push_back(c);
-      pl->large_cand.push_back(eup);
-      pl->large_free.push_back(nfree);
-      uint64_t slots = 0;
-      for (uint32_t i0 = beg; i0 < end; i0 += 32) {
-        uint32_t wmax = 0;
-        for (uint32_t i = i0; i < std::min(end, i0 + 32); ++i) wmax = std::max(wmax, row_ptr[comp_nodes[i] + 1] - row_ptr[comp_nodes[i]]);
-        slots += 32ull * ((wmax + 3u) & ~3u);  // slice width: a multiple of four slots (cta_block_row)
-      }
-      if (slots > 0xffffffffull) return fail(LFR_EUNSUPPORTED, "component too dense for the CTA tier's block layout");
-      pl->large_ell.push_back(slots);
-      return LFR_OK;
+  // Pass 1 — classify the slots [c0, c1): a pure function of the problem arrays that writes only the
+  // per-slot entries of its own range and its own accumulator, so ranges run on separate threads
+  // (merged in range order: the schedule does not depend on the thread count).
+  struct Acc {
+    Bucket caps[kKeys];
+    uint32_t count[kKeys] = {};
+    uint32_t n_solved = 0;
+    std::vector<uint32_t> large_slots, large_free;
+    std::vector<uint64_t> large_cand, large_ell;
+    int rc = LFR_OK;
+    const char* msg = nullptr;
+  };
+  auto classify = [&](uint32_t c0, uint32_t c1, Acc& A) {
+    auto bail = [&](int code, const char* m) {
+      A.rc = code;
+      A.msg = m;
     };
-    if (force_pcg || n2 > lfr::kMaxWarpN2 || nc > (uint32_t)lfr::kMaxWarpNodes || eup > 65535) {
-      LFR_TRY(to_cta_tier());
-      continue;
+    for (uint32_t c = c0; c < c1; ++c) {
+      const uint32_t beg = comp_ptr[c], end = comp_ptr[c + 1];
+      if (end < beg || end > pl->total_slots) return bail(LFR_EINVAL, "comp_ptr not monotone");
+      const uint32_t nc = end - beg;
+      pl->comp_size[c] = nc;
+      key_of[c] = kNoKey;
+      if (nc <= 1) continue;  // solve.cc:619-622
+      if (owner && owner[c] != pl->owner_id) continue;  // another device's component
+      ++A.n_solved;
+      uint64_t eup = 0;
+      uint32_t nfree = 0;
+      for (uint32_t i = beg; i < end; ++i) {
+        const uint32_t v = comp_nodes[i];
+        if (v >= n_nodes) return bail(LFR_EINVAL, "comp_nodes out of range");
+        const uint32_t r0 = row_ptr[v], r1 = row_ptr[v + 1];
+        if (r1 < r0) return bail(LFR_EINVAL, "row_ptr not monotone");
+        eup += r1 - r0;
+        nfree += is_root[v] ? 0 : 1;
+      }
+      const int n2 = std::max(2 * (int)nfree, 2);
+      auto to_cta_tier = [&]() -> bool {
+        if (nc > 16383) {
+          bail(LFR_EUNSUPPORTED, "component with more than 16383 nodes");
+          return false;
+        }
+        uint64_t slots = 0;
+        for (uint32_t i0 = beg; i0 < end; i0 += 32) {
+          uint32_t wmax = 0;
+          for (uint32_t i = i0; i < std::min(end, i0 + 32); ++i) wmax = std::max(wmax, row_ptr[comp_nodes[i] + 1] - row_ptr[comp_nodes[i]]);
+          slots += 32ull * ((wmax + 3u) & ~3u);  // slice width: a multiple of four slots (cta_block_row)
+        }
+        if (slots > 0xffffffffull) {
+          bail(LFR_EUNSUPPORTED, "component too dense for the CTA tier's block layout");
+          return false;
+        }
+        A.large_slots.push_back(c);
+        A.large_cand.push_back(eup);
+        A.large_free.push_back(nfree);
+        A.large_ell.push_back(slots);
+        return true;
+      };
+      if (force_pcg || n2 > lfr::kMaxWarpN2 || nc > (uint32_t)lfr::kMaxWarpNodes || eup > 65535) {
+        if (!to_cta_tier()) return;
+        continue;
+      }
+      const int e = std::max<int>(1, (int)eup);
+      int vi = (n2 <= 8) ? 0 : (n2 <= 16 ? 1 : (n2 <= 24 ? 2 : (n2 <= 32 ? 3 : (n2 <= 48 ? 5 : (n2 <= 64 ? 6 : (n2 <= 80 ? 7 : kV1))))));
+      if (vi <= 3 && n2 > tile_from && lfr::TileLayout(e, (int)nc, n2).total <= kMaxSmemPerBlock) vi = 4;
+      if (vi >= 5 && is_tile(vi) && (no_tile || lfr::TileLayout(e, (int)nc, n2).total > kMaxSmemPerBlock)) vi = kV1;
+      if (force_v1) vi = kV1;
+      int need = layout_bytes(vi, e, (int)nc, n2);
+      if (need > kMaxSmemPerBlock && vi != kV1) {  // the staged records do not fit: the Cholesky warp kernel reads them from global memory
+        vi = kV1;
+        need = layout_bytes(vi, e, (int)nc, n2);
+      }
+      if (need > kMaxSmemPerBlock) {
+        // a dense, high-degree component (its per-edge scratch alone exceeds one SM's shared
+        // memory): the CTA tier keeps its per-edge data in HBM
+        if (!to_cta_tier()) return;
+        continue;
+      }
+      int k = 0;
+      while (need > kClass[k]) ++k;  // need <= kClass[n_class - 1] here
+      const int key = vi * n_class + k;
+      key_of[c] = (uint16_t)key;
+      dim[c] = lfr_plan::SchedDim{e, (int)nc, n2};
+      Bucket& cb = A.caps[key];
+      ++A.count[key];
+      cb.emax = std::max(cb.emax, e);
+      cb.ncmax = std::max(cb.ncmax, (int)nc);
+      cb.n2max = std::max(cb.n2max, n2);
     }
-    const int e = std::max<int>(1, (int)eup);
-    int vi = (n2 <= 8) ? 0 : (n2 <= 16 ? 1 : (n2 <= 24 ? 2 : (n2 <= 32 ? 3 : (n2 <= 48 ? 5 : (n2 <= 64 ? 6 : (n2 <= 80 ? 7 : kV1))))));
-    if (vi <= 3 && n2 > tile_from && lfr::TileLayout(e, (int)nc, n2).total <= kMaxSmemPerBlock) vi = 4;
-    if (vi >= 5 && is_tile(vi) && (no_tile || lfr::TileLayout(e, (int)nc, n2).total > kMaxSmemPerBlock)) vi = kV1;
-    if (force_v1) vi = kV1;
-    int need = layout_bytes(vi, e, (int)nc, n2);
-    if (need > kMaxSmemPerBlock && vi != kV1) {  // the staged records do not fit: the Cholesky warp kernel reads them from global memory
-      vi = kV1;
-      need = layout_bytes(vi, e, (int)nc, n2);
+  };
+  // ranges of about equal node counts; extra threads only where their start-up pays
+  // (measured on the GPU box's host, profiles/r02_schedule_threads.txt: ~3 ns per listed node + ~16 ns
+  // per slot on one thread, ~50 us to start a helper)
+  const uint64_t work_ns = 3ull * pl->total_slots + 16ull * C;
+  int n_thr = (int)std::max<uint64_t>(1, std::min<uint64_t>(kScheduleThreadsMax, work_ns / 110000));
+  if (const char* e = std::getenv("LFR_SCHEDULE_THREADS")) n_thr = std::max(1, std::min(kScheduleThreadsMax, std::atoi(e)));
+  std::vector<uint32_t> cut((size_t)n_thr + 1, C);
+  cut[0] = 0;
+  for (int t = 1; t < n_thr; ++t) {
+    const uint32_t want = (uint32_t)((uint64_t)pl->total_slots * t / n_thr);
+    cut[t] = (uint32_t)(std::upper_bound(comp_ptr, comp_ptr + C + 1, want) - comp_ptr);
+    cut[t] = std::min(C, std::max(cut[t], cut[t - 1]));
+  }
+  std::vector<Acc> acc((size_t)n_thr);
+  {
+    std::vector<std::thread> workers;
+    for (int t = 1; t < n_thr; ++t) workers.emplace_back([&, t] { classify(cut[t], cut[t + 1], acc[t]); });
+    classify(cut[0], cut[1], acc[0]);
+    for (std::thread& w : workers) w.join();
+  }
+  Bucket caps[kKeys];
+  uint32_t count[kKeys] = {};
+  for (const Acc& A : acc) {  // range order
+    if (A.rc != LFR_OK) return fail(A.rc, A.msg);
+    pl->n_solved += A.n_solved;
+    for (int k = 0; k < kKeys; ++k) {
+      count[k] += A.count[k];
+      caps[k].emax = std::max(caps[k].emax, A.caps[k].emax);
+      caps[k].ncmax = std::max(caps[k].ncmax, A.caps[k].ncmax);
+      caps[k].n2max = std::max(caps[k].n2max, A.caps[k].n2max);
     }
-    if (need > kMaxSmemPerBlock) {
-      // a dense, high-degree component (its per-edge scratch alone exceeds one SM's shared
-      // memory): the CTA tier keeps its per-edge data in HBM
-      LFR_TRY(to_cta_tier());
-      continue;
-    }
-    int k = 0;
-    while (need > kClass[k]) ++k;  // need <= kClass[n_class - 1] here
-    const int key = vi * n_class + k;
-    key_of[c] = (uint16_t)key;
-    dim[c] = lfr_plan::SchedDim{e, (int)nc, n2};
-    Bucket& cb = caps[key];
-    ++count[key];
-    cb.emax = std::max(cb.emax, e);
-    cb.ncmax = std::max(cb.ncmax, (int)nc);
-    cb.n2max = std::max(cb.n2max, n2);
+    pl->large_slots.insert(pl->large_slots.end(), A.large_slots.begin(), A.large_slots.end());
+    pl->large_cand.insert(pl->large_cand.end(), A.large_cand.begin(), A.large_cand.end());
+    pl->large_free.insert(pl->large_free.end(), A.large_free.begin(), A.large_free.end());
+    pl->large_ell.insert(pl->large_ell.end(), A.large_ell.begin(), A.large_ell.end());
   }
   // emission order: largest shared-memory class first, within a class the higher tiers first
   uint32_t start[kKeys], total = 0;

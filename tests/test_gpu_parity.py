@@ -165,11 +165,12 @@ def test_fallback_tiers_match_oracle(b200, oracle, flags, cfg):
     _compare_dbg(b200, oracle, p, dbg)
 
 
-@pytest.mark.parametrize("cfg", ["cfg2", "cfg4"])
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg4", "ring60"])
 def test_staging_and_zero_copy_variants_are_bitwise_identical(b200, oracle, cfg):
     """The same solve with (a) TMA bulk staging from the caller's pinned buffers (zero-copy: edge
     records pulled over PCIe straight into shared memory, results written straight back), (b) the
-    same through HBM, (c) LDG -> STS staging: identical bits, all equal to the oracle to 1e-4 px."""
+    same through HBM, (c) LDG -> STS staging: identical bits, all equal to the oracle to 1e-4 px.
+    ring60 adds the CTA tier: its preparation kernel copies the kept records out of the pinned array."""
     import ctypes as C
     import torch
     from lfr_b200 import capi
@@ -503,6 +504,28 @@ def test_malformed_edges_are_reported(b200):
     # the library stays usable afterwards
     pos, st = b200.solve(p)
     assert st["n_solved"] > 0
+
+
+def test_malformed_edges_in_a_cta_tier_component_are_reported(b200):
+    """The CTA tier's lists are built on the device (cta_prepare_kernel): a bad destination inside a
+    large component raises the same LFR_EINVAL, through HBM and from pinned buffers."""
+    import copy
+    _, p = get_problem("ring60")
+    sizes = np.diff(p.comp_ptr.astype(np.int64))
+    c = int(np.argmax(sizes))
+    v = int(p.comp_nodes[p.comp_ptr[c]])
+    e0 = int(p.graph.row_ptr[v])
+    assert p.graph.row_ptr[v + 1] > e0
+    for bad_dst in (p.graph.n_nodes + 3, v):   # out of range, self edge
+        bad = copy.copy(p)
+        bad.graph = copy.copy(p.graph)
+        e = p.graph.edges.copy()
+        e["dst"][e0] = bad_dst
+        bad.graph.edges = e
+        with pytest.raises(RuntimeError, match=r"\(-1\)"):
+            b200.solve(bad)
+    pos, st = b200.solve(p)
+    assert st["n_solved"] > 0 and np.isfinite(pos).all()
 
 
 def test_option_variants(b200, oracle):
