@@ -201,6 +201,8 @@ struct lfr_plan {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_edges = nullptr;  // bulk edge copy done (only the non-staging tiers wait for it)
   cudaEvent_t ev_small = nullptr;  // fork / join of the second upload stream
+  cudaEvent_t ev_prep = nullptr;   // small arrays + local_of ready (CTA-tier preparation on the copy stream)
+  bool cta_from_hbm = false;       // zero-copy solve whose CTA tier reads the bulk HBM copy of the edge array
   cudaStream_t streams[kMaxStreams] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxStreams] = {};
   int n_streams = 0;
@@ -276,6 +278,7 @@ void free_plan(lfr_plan* pl) {
   if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
   if (pl->ev_edges) cudaEventDestroy(pl->ev_edges);
   if (pl->ev_small) cudaEventDestroy(pl->ev_small);
+  if (pl->ev_prep) cudaEventDestroy(pl->ev_prep);
   if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
   delete pl;
 }
@@ -429,7 +432,9 @@ int build_buckets(lfr_plan* pl, const lfr_problem* p) {
   // (measured on the GPU box's host, profiles/r02_schedule_threads.txt: ~3 ns per listed node + ~16 ns
   // per slot on one thread, ~50 us to start a helper)
   const uint64_t work_ns = 3ull * pl->total_slots + 16ull * C;
-  int n_thr = (int)std::max<uint64_t>(1, std::min<uint64_t>(kScheduleThreadsMax, work_ns / 110000));
+  // (inside an application the helpers cost more than in the stand-alone timing — the CUDA runtime
+  // hooks thread creation — so they start only from about half a millisecond of work)
+  int n_thr = work_ns < 500000 ? 1 : (int)std::min<uint64_t>(kScheduleThreadsMax, work_ns / 150000);
   if (const char* e = std::getenv("LFR_SCHEDULE_THREADS")) n_thr = std::max(1, std::min(kScheduleThreadsMax, std::atoi(e)));
   std::vector<uint32_t> cut((size_t)n_thr + 1, C);
   cut[0] = 0;
@@ -697,7 +702,14 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
       }
     if (scratch) LFR_TRY(pl->tile_scratch.reserve(sizeof(double) * scratch));
   }
-  if (zc_edges && pl->needs_hbm_edges) {
+  // Zero-copy and the CTA tier: its preparation kernel can pull the records it keeps straight from the
+  // pinned array, but SM loads over PCIe run at ~15 GB/s against ~50 GB/s for the copy engine
+  // (profiles/README.md), so that pays only while those components hold less than ~0.3 of the edges
+  // (one device of a multi-device solve); otherwise the whole array goes to HBM on the copy stream.
+  uint64_t cta_cand = 0;
+  for (uint64_t e : pl->large_cand) cta_cand += e;
+  pl->cta_from_hbm = zc_edges && 10 * cta_cand > 3 * (uint64_t)p->n_edges;
+  if (zc_edges && (pl->needs_hbm_edges || pl->cta_from_hbm)) {
     // mixed schedule: the Cholesky-warp tier reads edge records from global memory by index, so the
     // array goes to HBM after all — on its own stream, and only that tier waits for it
     if (!pl->copy_stream) LFR_CUDA(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
@@ -716,12 +728,23 @@ int fill_plan(lfr_plan* pl, const lfr_problem* p, const lfr_options& o, const do
   }
   if (pl->n_large) {
     // kept-edge records / in-edge lists, free-variable numbering and twins of the CTA-tier components,
-    // built on the device; with zero-copy edges the kernel pulls exactly the records these
-    // components keep from the caller's pinned array (no bulk copy of the edge array)
+    // built on the device; with zero-copy edges the kernel either pulls exactly the records these
+    // components keep from the caller's pinned array, or reads the bulk copy (see above)
     lfr::DevProblem P = pl->dev();
-    if (zc_edges) P.edges = zc_edges;
-    lfr::cta_prepare_kernel<<<pl->n_large, lfr::kCtaThreads, 0, s>>>(P, pl->cta_arrays(), pl->L_comps.as<lfr::CtaComp>());
+    cudaStream_t ps = s;
+    if (zc_edges && !pl->cta_from_hbm) {
+      P.edges = zc_edges;
+    } else if (zc_edges) {
+      // behind the bulk copy on the copy stream, once the small arrays and local_of (stream s) are
+      // there; the CTA-tier launches wait for ev_edges, the staging tiers do not
+      if (!pl->ev_prep) LFR_CUDA(cudaEventCreateWithFlags(&pl->ev_prep, cudaEventDisableTiming));
+      LFR_CUDA(cudaEventRecord(pl->ev_prep, s));
+      LFR_CUDA(cudaStreamWaitEvent(pl->copy_stream, pl->ev_prep, 0));
+      ps = pl->copy_stream;
+    }
+    lfr::cta_prepare_kernel<<<pl->n_large, lfr::kCtaThreads, 0, ps>>>(P, pl->cta_arrays(), pl->L_comps.as<lfr::CtaComp>());
     LFR_CUDA(cudaGetLastError());
+    if (ps != s) LFR_CUDA(cudaEventRecord(pl->ev_edges, pl->copy_stream));
   }
   // streams for concurrent bucket launches
   const int want = std::min<int>(kMaxStreams, std::max<int>(0, (int)pl->buckets.size() + (int)pl->cta_groups.size() - 1));
@@ -806,6 +829,7 @@ int launch_solve(lfr_plan* pl, cudaStream_t s) {
         bs = pl->streams[side++ % pl->n_streams];
         LFR_CUDA(cudaStreamWaitEvent(bs, pl->ev_fork, 0));
       }
+      if (pl->zc_edges && pl->cta_from_hbm) LFR_CUDA(cudaStreamWaitEvent(bs, pl->ev_edges, 0));
       // dynamic shared memory for the CG vectors of the group's largest component: the first
       // `smem_vecs` of p, w, r, z, y (2 doubles per free node each) and the preconditioner (3)
       const size_t per_node = (size_t)std::min(g.smem_vecs, 5) * 2 + (g.smem_vecs >= 6 ? 3 : 0);

@@ -47,7 +47,7 @@ def main():
             smem = num(r[idx["launch__shared_mem_per_block_dynamic"]]) * unit(
                 units[idx["launch__shared_mem_per_block_dynamic"]]) / 1e3
             f.write('"%s",%s,%s,%.3f,%.3f,%d,%d,%.3f\n' % (
-                name, grid, r[idx["launch__registers_per_thread"]], smem, dur, int(rd + wr),
+                name, grid, r[idx["launch__registers_per_thread"]], smem, dur, (int(rd + wr) if rd == rd and wr == wr else 0),
                 int(num(r[idx["smsp__inst_executed.sum"]])),
                 num(r[idx["sm__warps_active.avg.pct_of_peak_sustained_active"]])))
             if "solve_" in name:
