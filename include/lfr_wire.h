@@ -24,8 +24,10 @@ extern "C" {
 #endif
 
 /* Count image pairs and matches of one MatchingFile buffer (types.proto:3-28).
- * Returns 0, or LFR_EINVAL on malformed input ("Failed to parse proto object.",
- * solve.cc:433-436). */
+ * Walks the pair level only (a match is skipped by its length prefix); the
+ * contents of the matches are validated by lfr_wire_decode_matches.  Returns 0,
+ * or LFR_EINVAL on malformed input ("Failed to parse proto object.",
+ * solve.cc:433-436) — a buffer is well-formed iff scan AND decode return 0. */
 int lfr_wire_scan_matches(const uint8_t* buf, uint64_t len, uint64_t* n_pairs,
                           uint64_t* n_matches);
 

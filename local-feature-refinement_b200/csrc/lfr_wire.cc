@@ -1,7 +1,12 @@
 // lfr_wire.cc — protobuf wire codec for types.proto (MatchingFile,
 // SolutionFile) without libprotobuf.  Replaces the parse loop of
 // solve.cc:426-480 and the writer of solve.cc:643-679.  Host code only.
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "../../include/lfr.h"
 #include "../../include/lfr_wire.h"
@@ -85,16 +90,23 @@ bool read_match(Reader r, lfr_wire_matches* o, uint64_t m) {
     if (field == 1 && wt == 0) f1 = (uint32_t)r.varint();
     else if (field == 2 && wt == 0) f2 = (uint32_t)r.varint();
     else if (field == 3 && wt == 5) sim = r.f32();
-    else if (field == 4 && wt == 2) {
-      Reader d = r.sub();
-      if (!r.ok) return false;
-      if (!read_disp(d, (o && n1 < 9) ? o->disp1 + 18 * m + 2 * n1 : nullptr)) return false;
-      ++n1;
-    } else if (field == 5 && wt == 2) {
-      Reader d = r.sub();
-      if (!r.ok) return false;
-      if (!read_disp(d, (o && n2 < 9) ? o->disp2 + 18 * m + 2 * n2 : nullptr)) return false;
-      ++n2;
+    else if ((field == 4 || field == 5) && wt == 2) {
+      int& n = field == 4 ? n1 : n2;
+      float* dst = (o && n < 9) ? (field == 4 ? o->disp1 : o->disp2) + 18 * m + 2 * n : nullptr;
+      // the form every writer of this schema emits for a displacement with two non-zero floats:
+      // length 10, 0x0D <di>, 0x15 <dj> — taken without the generic field loop
+      if (r.end - r.p >= 11 && r.p[0] == 10 && r.p[1] == 0x0D && r.p[6] == 0x15) {
+        if (dst) {
+          std::memcpy(dst, r.p + 2, 4);
+          std::memcpy(dst + 1, r.p + 7, 4);
+        }
+        r.p += 11;
+      } else {
+        Reader d = r.sub();
+        if (!r.ok) return false;
+        if (!read_disp(d, dst)) return false;
+      }
+      ++n;
     } else r.skip(wt);
   }
   if (o) {
@@ -107,7 +119,9 @@ bool read_match(Reader r, lfr_wire_matches* o, uint64_t m) {
 
 // ImagePair { string image_name1 = 1; float fact1 = 2; string image_name2 = 3;
 //             float fact2 = 4; repeated Match matches = 5; }
-bool read_pair(Reader r, const uint8_t* base, lfr_wire_matches* o, uint64_t pair, uint64_t* m) {
+// count_only: match payloads are skipped by their length (their contents are validated by the decode)
+bool read_pair(Reader r, const uint8_t* base, lfr_wire_matches* o, uint64_t pair, uint64_t* m, bool count_only = false,
+               bool header_only = false) {
   if (o) {
     o->fact1[pair] = o->fact2[pair] = 0.f;
     o->name1_off[pair] = o->name2_off[pair] = 0;
@@ -128,6 +142,10 @@ bool read_pair(Reader r, const uint8_t* base, lfr_wire_matches* o, uint64_t pair
     else if (field == 5 && wt == 2) {
       Reader mm = r.sub();
       if (!r.ok) return false;
+      if (count_only || header_only) {
+        ++*m;
+        continue;
+      }
       if (o && *m >= o->n_matches) return false;
       if (!read_match(mm, o, *m)) return false;
       ++*m;
@@ -137,10 +155,27 @@ bool read_pair(Reader r, const uint8_t* base, lfr_wire_matches* o, uint64_t pair
 }
 
 // MatchingFile { repeated ImagePair image_pairs = 1; }
+// Matches of one pair only (its header fields were taken by the serial walk): used by the workers.
+bool read_pair_matches(Reader r, lfr_wire_matches* o, uint64_t m, uint64_t m_end) {
+  while (!r.done() && r.ok) {
+    const uint64_t tag = r.varint();
+    const uint32_t field = (uint32_t)(tag >> 3), wt = (uint32_t)(tag & 7);
+    if (field == 5 && wt == 2) {
+      Reader mm = r.sub();
+      if (!r.ok || m >= m_end) return false;
+      if (!read_match(mm, o, m)) return false;
+      ++m;
+    } else r.skip(wt);
+  }
+  return r.ok && m == m_end;
+}
+
 int walk_matching_file(const uint8_t* buf, uint64_t len, lfr_wire_matches* o, uint64_t* n_pairs,
                        uint64_t* n_matches) {
+  // serial walk over the pairs: header fields, match counts (match payloads skipped by length)
   Reader r{buf, buf + len};
   uint64_t pairs = 0, m = 0;
+  std::vector<Reader> pair_payload;
   while (!r.done() && r.ok) {
     const uint64_t tag = r.varint();
     const uint32_t field = (uint32_t)(tag >> 3), wt = (uint32_t)(tag & 7);
@@ -150,16 +185,40 @@ int walk_matching_file(const uint8_t* buf, uint64_t len, lfr_wire_matches* o, ui
       if (o) {
         if (pairs >= o->n_pairs) return LFR_EINVAL;
         o->pair_ptr[pairs] = m;
+        pair_payload.push_back(pr);
       }
-      if (!read_pair(pr, buf, o, pairs, &m)) return LFR_EINVAL;
+      if (!read_pair(pr, buf, o, pairs, &m, /*count_only=*/o == nullptr, /*header_only=*/o != nullptr)) return LFR_EINVAL;
       ++pairs;
     } else r.skip(wt);
   }
   if (!r.ok) return LFR_EINVAL;
-  if (o) o->pair_ptr[pairs] = m;
   if (n_pairs) *n_pairs = pairs;
   if (n_matches) *n_matches = m;
-  return LFR_OK;
+  if (!o) return LFR_OK;
+  if (m > o->n_matches) return LFR_EINVAL;
+  o->pair_ptr[pairs] = m;
+  // the matches of every pair, pairs dealt to worker threads (a pair's matches land at pair_ptr[pair]:
+  // the output does not depend on the thread count)
+  unsigned n_thr = 1;
+  if (len >= (4u << 20) && pairs > 1) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    n_thr = (unsigned)std::min<uint64_t>(std::min<uint64_t>(pairs, 8), hw ? hw : 1);
+    if (const char* e = std::getenv("LFR_WIRE_THREADS")) n_thr = (unsigned)std::max(1, std::min(64, std::atoi(e)));
+  }
+  std::atomic<uint64_t> next{0};
+  std::atomic<int> bad{0};
+  auto work = [&] {
+    for (;;) {
+      const uint64_t p = next.fetch_add(1);
+      if (p >= pairs || bad.load(std::memory_order_relaxed)) return;
+      if (!read_pair_matches(pair_payload[p], o, o->pair_ptr[p], o->pair_ptr[p + 1])) bad.store(1);
+    }
+  };
+  std::vector<std::thread> helpers;
+  for (unsigned t = 1; t < n_thr; ++t) helpers.emplace_back(work);
+  work();
+  for (std::thread& h : helpers) h.join();
+  return bad.load() ? LFR_EINVAL : LFR_OK;
 }
 
 // ---- encoder ----------------------------------------------------------------------

@@ -70,6 +70,56 @@ def test_unknown_fields_are_skipped_and_garbage_is_rejected(small_ms):
     assert wire.decode_matching_file(b"").n_pairs == 0
 
 
+def test_displacement_encodings_other_than_the_canonical_one():
+    """The decoder takes a shortcut for the usual 10-byte displacement (di then dj, both non-zero); every
+    other legal encoding goes through the generic field loop: dj before di, a zero field omitted, an
+    unknown field inside, an empty displacement, a repeated field (last value wins)."""
+    import struct
+
+    def f32(tag, v):
+        return bytes([tag]) + struct.pack("<f", v)
+
+    def lenpref(tag, payload):
+        assert len(payload) < 128
+        return bytes([tag, len(payload)]) + payload
+
+    disps = [f32(0x0D, 1.5) + f32(0x15, -2.5),            # canonical
+             f32(0x15, 4.0) + f32(0x0D, 3.0),             # dj first
+             f32(0x0D, 5.0),                              # dj omitted (zero)
+             f32(0x15, 6.0),                              # di omitted
+             b"",                                         # both zero
+             f32(0x0D, 7.0) + bytes([0x18, 0x2A]) + f32(0x15, 8.0),   # unknown varint field 3 in between
+             f32(0x0D, 9.0) + f32(0x0D, 10.0) + f32(0x15, 11.0)]     # di twice: the last one counts
+    match = bytes([0x08, 3, 0x10, 4]) + f32(0x1D, 0.75) + b"".join(lenpref(0x22, d) for d in disps) \
+        + lenpref(0x2A, f32(0x0D, -1.0) + f32(0x15, -3.0))
+    pair = lenpref(0x0A, b"x") + f32(0x15, 2.0) + lenpref(0x1A, b"y") + f32(0x25, 4.0) + lenpref(0x2A, match)
+    data = lenpref(0x0A, pair)
+    ms = wire.decode_matching_file(data)
+    assert ms.n_matches == 1 and int(ms.feat1[0]) == 3 and int(ms.feat2[0]) == 4 and float(ms.sim[0]) == 0.75
+    assert ms.disp1[0, :14].tolist() == [1.5, -2.5, 3.0, 4.0, 5.0, 0.0, 0.0, 6.0, 0.0, 0.0, 7.0, 8.0, 10.0, 11.0]
+    assert ms.disp2[0, :2].tolist() == [-1.0, -3.0] and np.all(ms.disp2[0, 2:] == 0)
+    mf = MatchingFile()
+    mf.ParseFromString(data)                              # python-protobuf agrees
+    got = [(d.di, d.dj) for d in mf.image_pairs[0].matches[0].disp1]
+    assert got == [(1.5, -2.5), (3.0, 4.0), (5.0, 0.0), (0.0, 6.0), (0.0, 0.0), (7.0, 8.0), (10.0, 11.0)]
+
+
+def test_garbage_inside_a_match_is_rejected(small_ms):
+    """The pair-level scan skips matches by their length; their contents are checked by the decode."""
+    data = bytearray(wire.encode_matching_file(small_ms))
+    ms = small_ms
+    # corrupt the first displacement of the first match: claim a length that runs past the match
+    i = data.index(bytes([0x22, 0x0A, 0x0D]))
+    data[i + 1] = 0x7F
+    with pytest.raises(wire.ParseError):
+        wire.decode_matching_file(bytes(data))
+    # a big file (several worker threads): every pair decoded into its own range
+    big = synth.generate("cfg2", scale=0.5)
+    blob = wire.encode_matching_file(big)
+    assert len(blob) > (4 << 20)
+    _assert_same(wire.decode_matching_file(blob), big)
+
+
 def test_part_files(tmp_path, small_ms):
     """`.part.N` every k pairs (compute_match_graph.py:78,189-205), read back like solve.cc:416-424."""
     path = str(tmp_path / "m.pb")
