@@ -7,7 +7,11 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <condition_variable>
 #include <map>
 #include <thread>
 #include <numeric>
@@ -163,47 +167,116 @@ std::vector<uint32_t> connected_components(uint32_t n, const std::vector<uint32_
 // graph.py::recursive_cut (solve.cc:185-250 as a work list): split until every group weighs
 // <= max_weight (node weight = nodes of the track, solve.cc:198) or has no internal edge (then its
 // nodes become singleton groups, solve.cc:240-246).  The 2-way cut itself is lfr_cut.h.
-void recursive_cut(std::vector<lfr::CutEdge> edges0, const std::vector<uint32_t>& node_weight, uint32_t max_weight,
-                   lfr::CutWorkspace& W, std::vector<std::vector<uint32_t>>* groups) {
-  std::vector<std::vector<lfr::CutEdge>> work;
-  work.push_back(std::move(edges0));
-  std::vector<uint8_t> covered;
-  while (!work.empty()) {
-    const std::vector<lfr::CutEdge> edges = std::move(work.back());
-    work.pop_back();
-    lfr::two_way_cut(edges.data(), edges.size(), W);
-    const uint32_t n = (uint32_t)W.nodes.size();
-    std::vector<lfr::CutEdge> sub[2];
-    for (int s = 0; s < 2; ++s) {
-      std::vector<uint32_t> members;
-      int64_t w = 0;
-      for (uint32_t i = 0; i < n; ++i)
-        if (W.side[i] == s) {
-          members.push_back(W.nodes[i]);  // ascending
-          w += node_weight[W.nodes[i]];
-        }
-      if (members.empty()) continue;
-      if (w <= (int64_t)max_weight) {
-        groups->push_back(std::move(members));  // solve.cc:205-211
-        continue;
+// One step: cut `edges`, emit the finished groups, return the edge lists of the two sides that
+// have to be cut again (empty when done).  A pure function of `edges` (in their order).
+void cut_step(const std::vector<lfr::CutEdge>& edges, const std::vector<uint32_t>& node_weight, uint32_t max_weight,
+              lfr::CutWorkspace& W, std::vector<uint8_t>& covered, std::vector<std::vector<uint32_t>>* groups,
+              std::vector<lfr::CutEdge> (&sub)[2]) {
+  lfr::two_way_cut(edges.data(), edges.size(), W);
+  const uint32_t n = (uint32_t)W.nodes.size();
+  for (int s = 0; s < 2; ++s) {
+    sub[s].clear();
+    std::vector<uint32_t> members;
+    int64_t w = 0;
+    for (uint32_t i = 0; i < n; ++i)
+      if (W.side[i] == s) {
+        members.push_back(W.nodes[i]);  // ascending
+        w += node_weight[W.nodes[i]];
       }
-      covered.assign(n, 0);
-      for (const lfr::CutEdge& e : edges) {
-        const int32_t la = W.local[e.a], lb = W.local[e.b];
-        if (W.side[la] == s && W.side[lb] == s) {
-          sub[s].push_back(e);
-          covered[la] = 1;
-          covered[lb] = 1;
-        }
-      }
-      for (uint32_t x : members)  // no edge left inside the subset: singleton groups
-        if (!covered[W.local[x]]) groups->push_back(std::vector<uint32_t>(1, x));
+    if (members.empty()) continue;
+    if (w <= (int64_t)max_weight) {
+      groups->push_back(std::move(members));  // solve.cc:205-211
+      continue;
     }
-    lfr::cut_release(W);
-    // side 0 is processed before side 1 (the work list is a stack)
-    if (!sub[1].empty()) work.push_back(std::move(sub[1]));
-    if (!sub[0].empty()) work.push_back(std::move(sub[0]));
+    covered.assign(n, 0);
+    for (const lfr::CutEdge& e : edges) {
+      const int32_t la = W.local[e.a], lb = W.local[e.b];
+      if (W.side[la] == s && W.side[lb] == s) {
+        sub[s].push_back(e);
+        covered[la] = 1;
+        covered[lb] = 1;
+      }
+    }
+    for (uint32_t x : members)  // no edge left inside the subset: singleton groups
+      if (!covered[W.local[x]]) groups->push_back(std::vector<uint32_t>(1, x));
   }
+  lfr::cut_release(W);
+}
+
+// All oversized meta-components, cut down to groups.  The groups form a partition that does not
+// depend on the order in which the sub-problems are processed (each cut is a function of its own edge
+// list only), so the work list is shared by a few threads; only membership is used afterwards.
+void recursive_cut_all(std::vector<std::vector<lfr::CutEdge>> roots, const std::vector<uint32_t>& node_weight,
+                       uint32_t max_weight, std::vector<std::vector<uint32_t>>* groups) {
+  uint64_t total_edges = 0;
+  for (const auto& r : roots) total_edges += r.size();
+  unsigned n_thr = 1;
+  if (total_edges >= 2048) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    n_thr = std::min(8u, hw ? hw : 1u);
+  }
+  if (const char* e = std::getenv("LFR_HOST_THREADS")) n_thr = (unsigned)std::max(1, std::min(64, std::atoi(e)));
+  std::vector<std::vector<lfr::CutEdge>> work;
+  for (auto it = roots.rbegin(); it != roots.rend(); ++it) work.push_back(std::move(*it));
+  if (n_thr <= 1) {
+    lfr::CutWorkspace W;
+    std::vector<uint8_t> covered;
+    std::vector<lfr::CutEdge> sub[2];
+    while (!work.empty()) {
+      const std::vector<lfr::CutEdge> edges = std::move(work.back());
+      work.pop_back();
+      cut_step(edges, node_weight, max_weight, W, covered, groups, sub);
+      if (!sub[1].empty()) work.push_back(std::move(sub[1]));
+      if (!sub[0].empty()) work.push_back(std::move(sub[0]));
+    }
+    return;
+  }
+  // shared list: sub-problems of at least kShare edges (a handful per scene: the top of each recursion
+  // tree); anything smaller is finished by the thread that produced it, on its own stack
+  constexpr size_t kShare = 1024;
+  std::mutex mu;
+  std::condition_variable cv;
+  unsigned active = 0;
+  std::vector<std::vector<std::vector<uint32_t>>> found(n_thr);
+  auto worker = [&](unsigned t) {
+    lfr::CutWorkspace W;
+    std::vector<uint8_t> covered;
+    std::vector<lfr::CutEdge> sub[2];
+    std::vector<std::vector<lfr::CutEdge>> mine;
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv.wait(lk, [&] { return !work.empty() || active == 0; });
+      if (work.empty()) return;  // and nobody is producing more
+      mine.push_back(std::move(work.back()));
+      work.pop_back();
+      ++active;
+      lk.unlock();
+      while (!mine.empty()) {
+        const std::vector<lfr::CutEdge> edges = std::move(mine.back());
+        mine.pop_back();
+        cut_step(edges, node_weight, max_weight, W, covered, &found[t], sub);
+        for (int sd = 1; sd >= 0; --sd) {
+          if (sub[sd].empty()) continue;
+          if (sub[sd].size() >= kShare) {
+            std::lock_guard<std::mutex> g(mu);
+            work.push_back(std::move(sub[sd]));
+            cv.notify_one();
+          } else {
+            mine.push_back(std::move(sub[sd]));
+          }
+        }
+      }
+      lk.lock();
+      --active;
+      cv.notify_all();
+    }
+  };
+  std::vector<std::thread> helpers;
+  for (unsigned t = 1; t < n_thr; ++t) helpers.emplace_back(worker, t);
+  worker(0);
+  for (std::thread& h : helpers) h.join();
+  for (auto& f : found)
+    for (auto& g : f) groups->push_back(std::move(g));
 }
 
 }  // namespace
@@ -556,6 +629,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
       wsum[i] = sums[idx[i]];
     }
   }
+  const double t_meta = ms_since(t_cut);
   uint32_t n_cc = 0;
   const std::vector<uint32_t> cc = connected_components(T, ma, mb, nullptr, &n_cc);
   S.n_meta_components = n_cc;
@@ -579,17 +653,15 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
       if (s < 0) continue;
       per_cc[s].push_back(lfr::CutEdge{ma[i], mb[i], (int64_t)(int)(100.0 * wsum[i])});  // static_cast<int>(100 * it.second), solve.cc:329
     }
-    lfr::CutWorkspace W;
-    for (auto& edges : per_cc) {
-      std::vector<std::vector<uint32_t>> groups;
-      recursive_cut(std::move(edges), nodes_in_track, max_nodes, W, &groups);
-      for (const auto& g : groups) {
-        for (uint32_t t : g) gc[t] = next_label;
-        ++next_label;
-      }
-      S.n_cut_groups += (uint32_t)groups.size();
+    std::vector<std::vector<uint32_t>> groups;
+    recursive_cut_all(std::move(per_cc), nodes_in_track, max_nodes, &groups);
+    for (const auto& g : groups) {  // labels only say "same group": their order is irrelevant
+      for (uint32_t t : g) gc[t] = next_label;
+      ++next_label;
     }
+    S.n_cut_groups += (uint32_t)groups.size();
   }
+  const double t_rec = ms_since(t_cut);
   std::vector<uint8_t> keep(ma.size());
   for (size_t i = 0; i < ma.size(); ++i) keep[i] = gc[ma[i]] == gc[mb[i]];
   uint32_t n_final = 0;
@@ -598,6 +670,9 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   for (uint32_t v = 0; v < N; ++v) hs->comp[v] = final_cc[hs->track[v]];
   hs->C = n_final;
   S.graph_cut_ms = ms_since(t_cut);
+  if (std::getenv("LFR_HOST_TIMING"))
+    std::fprintf(stderr, "graph cut: meta-graph %.2f ms, cc + recursive cut %.2f ms (oversized %zu, groups %u), final cc %.2f ms; meta edges %zu\n",
+                 t_meta, t_rec - t_meta, per_cc.size(), S.n_cut_groups, S.graph_cut_ms - t_rec, ma.size());
   const auto t_disp = Clock::now();
   // ---- H5: dispatch list (solve.cc:594-604) ----------------------------------------------------
   std::vector<uint32_t> sizes(n_final, 0);
