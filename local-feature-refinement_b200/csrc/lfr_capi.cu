@@ -1153,7 +1153,8 @@ int lfr_debug_last_solve_profile(int device, unsigned long long* cycles, unsigne
 }
 
 // host-only: best-of-`reps` time of the schedule construction (build_buckets), no device needed
-int lfr_debug_time_schedule(const lfr_problem* p, const lfr_options* opt, int reps, double* best_us, int* n_launches) {
+int lfr_debug_time_schedule(const lfr_problem* p, const lfr_options* opt, int reps, double* best_us, int* n_launches,
+                            uint64_t* digest) {
   if (!p || !best_us) return fail(LFR_EINVAL, "null argument");
   LFR_TRY(validate(p));
   lfr_plan pl;
@@ -1190,6 +1191,25 @@ int lfr_debug_time_schedule(const lfr_problem* p, const lfr_options* opt, int re
       std::fprintf(stderr, "bucket variant %3d  n %6u  emax %5d ncmax %4d n2max %3d  smem/warp %6d  warps %d  -> CTAs/SM by smem %d\n", b.variant,
                    b.n, b.emax, b.ncmax, b.n2max, b.smem_per_warp, b.warps, (int)(kMaxSmemPerBlock / (b.smem_per_warp * b.warps + 1024)));
     std::fprintf(stderr, "CTA tier: %zu components\n", pl.large_slots.size());
+  }
+  if (digest) {  // FNV-1a over everything the launches depend on: the schedule must not depend on the thread count
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) {
+      for (int i = 0; i < 8; ++i) {
+        h ^= (v >> (8 * i)) & 0xff;
+        h *= 1099511628211ull;
+      }
+    };
+    mix(pl.n_solved);
+    for (const Bucket& b : pl.buckets) {
+      mix(b.offset); mix(b.n); mix((uint64_t)b.emax); mix((uint64_t)b.ncmax); mix((uint64_t)b.n2max);
+      mix((uint64_t)b.smem_per_warp); mix((uint64_t)b.warps); mix((uint64_t)b.variant);
+    }
+    for (uint32_t c : pl.list_host) mix(c);
+    for (size_t i = 0; i < pl.large_slots.size(); ++i) {
+      mix(pl.large_slots[i]); mix(pl.large_cand[i]); mix(pl.large_free[i]); mix(pl.large_ell[i]);
+    }
+    *digest = h;
   }
   *best_us = best;
   if (n_launches) *n_launches = (int)pl.buckets.size() + (pl.large_slots.empty() ? 0 : 1);  // (CTA tier counted once here)

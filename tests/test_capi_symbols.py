@@ -104,3 +104,22 @@ def test_oracle_exports_solve_multi_with_single_device_semantics(oracle):
     pos1, st1 = oracle.solve(p, oracle.default_options(n_threads=2))
     pos2, st2 = oracle.solve_multi(p, [0, 1], oracle.default_options(n_threads=2))
     assert np.array_equal(pos1, pos2) and np.array_equal(st1["iterations"], st2["iterations"])
+
+
+def test_schedule_does_not_depend_on_the_thread_count(b200, monkeypatch):
+    """The launch schedule (buckets, launch lists, CTA-tier components) is built on the host by range
+    workers for large dispatch lists; merged in range order, it must be the same for any thread count.
+    (Host-only hook of the product library: no device involved.)"""
+    from lfr_b200 import build_problem, synth
+    f = b200.lib.lfr_debug_time_schedule
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    for name, scale in (("cfg3", 1.0), ("ring60", 1.0), ("cfg5", 0.05)):
+        p = build_problem(synth.generate(name, scale=scale))
+        s, keep = b200.marshal(p)
+        seen = set()
+        for n_thr in ("1", "2", "5", "8"):
+            monkeypatch.setenv("LFR_SCHEDULE_THREADS", n_thr)
+            us, nl, dg = C.c_double(), C.c_int(), C.c_uint64()
+            assert f(C.byref(s), None, 1, C.byref(us), C.byref(nl), C.byref(dg)) == 0
+            seen.add((nl.value, dg.value))
+        assert len(seen) == 1, (name, seen)

@@ -7,5 +7,5 @@ for cfg in sys.argv[1:] or ['cfg2']:
     p=build_problem(synth.generate(cfg))
     s,arrays=lib.marshal(p)
     us=C.c_double(); nl=C.c_int()
-    f=lib.lib.lfr_debug_time_schedule; f.argtypes=[C.c_void_p,C.c_void_p,C.c_int,C.POINTER(C.c_double),C.POINTER(C.c_int)]
-    rc=f(C.byref(s),None,50,C.byref(us),C.byref(nl)); print(cfg,'rc',rc,'schedule us',us.value,'launches',nl.value)
+    f=lib.lib.lfr_debug_time_schedule; f.argtypes=[C.c_void_p,C.c_void_p,C.c_int,C.POINTER(C.c_double),C.POINTER(C.c_int),C.c_void_p]
+    rc=f(C.byref(s),None,50,C.byref(us),C.byref(nl),None); print(cfg,'rc',rc,'schedule us',us.value,'launches',nl.value)
