@@ -195,6 +195,13 @@ int lfr_solve_multi(const lfr_problem* p, const lfr_options* o, const int32_t* d
  * releases them all; a later call simply re-creates what it needs.  No-op in the oracle. */
 void lfr_shutdown(void);
 
+/* Page-locked host memory for the arrays handed to lfr_solve() / lfr_solve_multi(): `edges` and
+ * `positions` allocated here are used in place (zero-copy, see lfr_solve).  Returns NULL when the
+ * allocation fails or there is no CUDA device — the caller may then use ordinary memory (the solve
+ * still needs a device).  The oracle returns ordinary aligned memory.  Free with lfr_host_free(). */
+void* lfr_host_alloc(uint64_t bytes);
+void lfr_host_free(void* p);
+
 /* ---- device-resident plan (b200 only; the oracle returns LFR_EUNSUPPORTED) --
  * lfr_plan_create copies the problem to HBM once; lfr_plan_solve re-runs the
  * whole solve from the stored initial positions, asynchronously on `stream`

@@ -71,7 +71,7 @@ class LfrMultiInfo(C.Structure):
 
 #: every symbol include/lfr.h declares
 ABI_SYMBOLS = [
-    "lfr_abi_version", "lfr_backend", "lfr_last_error", "lfr_options_default", "lfr_solve", "lfr_solve_multi", "lfr_shutdown",
+    "lfr_abi_version", "lfr_backend", "lfr_last_error", "lfr_options_default", "lfr_solve", "lfr_solve_multi", "lfr_shutdown", "lfr_host_alloc", "lfr_host_free",
     "lfr_plan_create", "lfr_plan_solve", "lfr_plan_download", "lfr_plan_num_launches",
     "lfr_plan_traffic", "lfr_plan_destroy", "lfr_debug_edge_eval",
 ]

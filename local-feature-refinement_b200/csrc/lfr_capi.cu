@@ -1249,6 +1249,19 @@ int lfr_solve(const lfr_problem* p, const lfr_options* opt, double* positions, l
   return solve_on_device(p, o, positions, st, nullptr, 0, nullptr);
 }
 
+void* lfr_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? (size_t)bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void lfr_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 void lfr_shutdown(void) {
   // release the cached per-device workspaces of lfr_solve() / lfr_solve_multi() (device buffers,
   // pinned staging, streams, events); the next call re-creates what it needs

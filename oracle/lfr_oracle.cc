@@ -1070,6 +1070,9 @@ int lfr_solve_multi(const lfr_problem* p, const lfr_options* opt, const int32_t*
 
 void lfr_shutdown(void) {}
 
+void* lfr_host_alloc(uint64_t bytes) { return std::aligned_alloc(64, ((size_t)bytes + 63) / 64 * 64 + 64); }
+void lfr_host_free(void* p) { std::free(p); }
+
 int lfr_plan_create(const lfr_problem*, const lfr_options*, const double*, lfr_plan**) {
   return fail(LFR_EUNSUPPORTED, "cpu-oracle has no device plans");
 }
