@@ -112,6 +112,8 @@ inline uint32_t sortable_bits(float f) {
 void sort_matches(const std::vector<uint32_t>& key, const std::vector<uint32_t>& n1, const std::vector<uint32_t>& n2,
                   std::vector<uint32_t>* order_out) {
   const size_t M = key.size();
+  // (sorting (key, index) pairs instead, so that a pass streams its input, was measured slower: twice the
+  // bytes through the scatter)
   std::vector<uint32_t> a(M), b(M);
   std::iota(a.begin(), a.end(), 0u);
   for (int pass = 0; pass < 3; ++pass) {
@@ -371,6 +373,10 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     ++hs->row_ptr[n2[k] + 1];
   }
   for (uint32_t v = 0; v < N; ++v) hs->row_ptr[v + 1] += hs->row_ptr[v];
+  // destination and similarity of every directed edge once more, 8 bytes per edge: the root scores and
+  // the track meta-graph below walk all edges three times and need nothing else of the 80-byte records
+  std::vector<uint32_t> cdst;
+  std::vector<float> csim;
   if (in->edges_out && in->edges_out_capacity >= 2 * M) {
     hs->edges.borrow(in->edges_out, 2 * M);
   } else if (!hs->edges.alloc(2 * M)) {
@@ -382,6 +388,8 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     // solve.cc:477-478): sequential; the 80-byte record copies then run on several threads
     std::vector<uint32_t> fill(hs->row_ptr.begin(), hs->row_ptr.end() - (N ? 1 : 0));
     std::vector<uint32_t> slot1(M), slot2(M);
+    cdst.resize(2 * M);
+    csim.resize(2 * M);
     for (uint64_t k = 0; k < M; ++k) {
       slot1[k] = fill[n1[k]]++;
       slot2[k] = fill[n2[k]]++;
@@ -397,6 +405,10 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
         std::memcpy(e2.flow, in->disp1 + 18 * m, 18 * sizeof(float));   // n2 -> n1 carries disp1
         e2.sim = in->sim[m];
         e2.dst = n1[k];
+        cdst[slot1[k]] = n2[k];
+        csim[slot1[k]] = in->sim[m];
+        cdst[slot2[k]] = n1[k];
+        csim[slot2[k]] = in->sim[m];
       }
     };
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -425,6 +437,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     for (uint64_t k = 0; k < M; ++k) key[k] = sortable_bits(in->sim[kept_matches[k]]);
     sort_matches(key, n1, n2, &order);
   }
+  const double t_sorted = ms_since(t_tracks);
   std::vector<int32_t> parent(N, -1);
   if (in->n_images > 65535) {
     delete hs;
@@ -559,6 +572,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
       absorb(r1, r2);
     }
   }
+  const double t_union = ms_since(t_tracks);
   hs->track.assign(N, 0);
   uint32_t T = 0;
   for (uint32_t v = 0; v < N; ++v)
@@ -569,6 +583,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   std::vector<uint32_t> nodes_in_track(T, 0);
   for (uint32_t v = 0; v < N; ++v) ++nodes_in_track[hs->track[v]];
   S.max_track_size = *std::max_element(nodes_in_track.begin(), nodes_in_track.end());
+  const double t_ids = ms_since(t_tracks);
   // ---- H3: roots (solve.cc:552-582) -----------------------------------------------------------
   hs->is_root.assign(N, 0);
   {
@@ -578,7 +593,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     for (uint32_t v = 0; v < N; ++v) {
       double score = 0.0;
       for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e)
-        if (hs->track[v] == hs->track[hs->edges[e].dst]) score += (double)hs->edges[e].sim;
+        if (hs->track[v] == hs->track[cdst[e]]) score += (double)csim[e];
       const uint32_t t = hs->track[v];
       if (!has[t] || score > best_score[t] || (score == best_score[t] && v > best_node[t])) {
         has[t] = 1;
@@ -589,6 +604,9 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     for (uint32_t t = 0; t < T; ++t) hs->is_root[best_node[t]] = 1;
   }
   S.tracks_ms = ms_since(t_tracks);
+  if (std::getenv("LFR_HOST_TIMING"))
+    std::fprintf(stderr, "tracks: sort %.1f ms, union-find %.1f ms, track ids %.1f ms, roots %.1f ms\n", t_sorted, t_union - t_sorted,
+                 t_ids - t_union, S.tracks_ms - t_ids);
   const auto t_cut = Clock::now();
   // ---- H4: meta-graph, connected components, size-capped cut (solve.cc:252-373) -------------
   std::vector<uint32_t> ma, mb;
@@ -596,14 +614,14 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   {
     uint64_t n_inter = 0;
     for (uint32_t v = 0; v < N; ++v)
-      for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e) n_inter += hs->track[v] != hs->track[hs->edges[e].dst];
+      for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e) n_inter += hs->track[v] != hs->track[cdst[e]];
     FlatMap slot((size_t)n_inter);
     std::vector<uint64_t> keys;
     std::vector<double> sums;
     for (uint32_t v = 0; v < N; ++v) {
       const uint32_t ts = hs->track[v];
       for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e) {
-        const uint32_t tt = hs->track[hs->edges[e].dst];
+        const uint32_t tt = hs->track[cdst[e]];
         if (ts == tt) continue;
         const uint64_t key = (uint64_t)ts * T + tt;
         bool fresh;
@@ -611,9 +629,9 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
         if (fresh) {
           slot.vals[sl] = (uint32_t)keys.size();
           keys.push_back(key);
-          sums.push_back((double)hs->edges[e].sim);
+          sums.push_back((double)csim[e]);
         } else {
-          sums[slot.vals[sl]] += (double)hs->edges[e].sim;  // accumulation in node / out-edge order
+          sums[slot.vals[sl]] += (double)csim[e];  // accumulation in node / out-edge order
         }
       }
     }
