@@ -107,3 +107,21 @@ def test_banned_images_and_empty_input():
     assert "0001.png" not in names
     p0 = build_problem(ms, banned_images=ms.image_names)
     assert p0.graph.n_nodes == 0 and p0.n_components == 0
+
+
+@pytest.mark.parametrize("cfg,scale", [("cfg2", 1.0), ("cfg4", 0.3), ("cfg5", 0.03)])
+def test_native_host_stage_does_not_depend_on_the_thread_count(cfg, scale, monkeypatch):
+    """The recursive cut shares its large sub-problems between threads, the edge records are copied by
+    several threads: every output array is the same for 1, 3 and 8 of them."""
+    ms = synth.generate(cfg, scale=scale)
+    ref = None
+    for n_thr in ("1", "3", "8"):
+        monkeypatch.setenv("LFR_HOST_THREADS", n_thr)
+        p = build_problem(ms, native=True)
+        got = [p.track, p.comp, p.is_root, p.comp_ptr, p.comp_nodes, p.comp_order, p.graph.row_ptr,
+               p.graph.edges.view(np.uint8), np.array([p.info[k] for k in ("n_tracks", "n_components", "n_cut_groups")])]
+        if ref is None:
+            ref = got
+        else:
+            for a, b in zip(ref, got):
+                assert np.array_equal(a, b)
