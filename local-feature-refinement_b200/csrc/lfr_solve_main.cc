@@ -257,7 +257,7 @@ int main(int argc, char** argv) {
   }
   {
     uint64_t p0 = 0, m0 = 0;
-    for (const Part& pt : parts) {
+    for (Part& pt : parts) {
       for (uint64_t p = 0; p < pt.P; ++p) {
         pair_img1[p0 + p] = intern(pt, pt.n1_off[p], pt.n1_len[p]);
         pair_img2[p0 + p] = intern(pt, pt.n2_off[p], pt.n2_len[p]);
@@ -274,6 +274,14 @@ int main(int argc, char** argv) {
       }
       p0 += pt.P;
       m0 += pt.M;
+      std::vector<uint8_t>().swap(pt.buf);  // the file image (7 GB at Madrid scale) is not needed past the names
+      if (cat) {
+        std::vector<uint32_t>().swap(pt.feat1);
+        std::vector<uint32_t>().swap(pt.feat2);
+        std::vector<float>().swap(pt.sim);
+        std::vector<float>().swap(pt.disp1);
+        std::vector<float>().swap(pt.disp2);
+      }
     }
   }
   const uint32_t* feat1 = cat ? feat1_cat.data() : (parts.empty() ? nullptr : parts[0].feat1.data());
