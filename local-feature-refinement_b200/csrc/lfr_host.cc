@@ -115,13 +115,24 @@ void sort_matches(const std::vector<uint32_t>& key, const std::vector<uint32_t>&
   // (sorting (key, index) pairs instead, so that a pass streams its input, was measured slower: twice the
   // bytes through the scatter)
   std::vector<uint32_t> a(M), b(M);
-  std::iota(a.begin(), a.end(), 0u);
+  // all three histograms in one sequential sweep over the keys; the first pass reads them in place
+  // (its input order is the identity), only the other two gather key[a[i]]
+  std::vector<uint32_t> hist(3 * 2049, 0);
+  for (size_t i = 0; i < M; ++i) {
+    const uint32_t k = key[i];
+    ++hist[(k & 2047u) + 1];
+    ++hist[2049 + ((k >> 11) & 2047u) + 1];
+    ++hist[2 * 2049 + ((k >> 22) & 2047u) + 1];
+  }
   for (int pass = 0; pass < 3; ++pass) {
+    uint32_t* h = &hist[pass * 2049];
+    for (int d = 0; d < 2048; ++d) h[d + 1] += h[d];
+  }
+  for (size_t i = 0; i < M; ++i) a[hist[key[i] & 2047u]++] = (uint32_t)i;
+  for (int pass = 1; pass < 3; ++pass) {
     const int shift = 11 * pass;
-    uint32_t hist[2049] = {0};
-    for (size_t i = 0; i < M; ++i) ++hist[((key[a[i]] >> shift) & 2047u) + 1];
-    for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
-    for (size_t i = 0; i < M; ++i) b[hist[(key[a[i]] >> shift) & 2047u]++] = a[i];
+    uint32_t* h = &hist[pass * 2049];
+    for (size_t i = 0; i < M; ++i) b[h[(key[a[i]] >> shift) & 2047u]++] = a[i];
     a.swap(b);
   }
   for (size_t i = 0; i < M;) {
@@ -438,7 +449,14 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     sort_matches(key, n1, n2, &order);
   }
   const double t_sorted = ms_since(t_tracks);
-  std::vector<int32_t> parent(N, -1);
+  // union-find node: parent link and, for roots, the image set (size; list / bitset slot) in one 12-byte record —
+  // the root reached by find() is the line the set tests need next
+  struct UfNode {
+    int32_t parent;  // -1 = root
+    uint32_t size;   // images in the set of this root (more than 64 images)
+    int32_t slot;    // index into lists (size <= kListMax) or bitsets (above), -1 = singleton
+  };
+  std::vector<UfNode> uf(N, UfNode{-1, 1, -1});
   if (in->n_images > 65535) {
     delete hs;
     return LFR_EUNSUPPORTED;
@@ -449,42 +467,40 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   // a short sorted list up to kListMax entries, then a bitset of n_images bits from a pool
   const uint32_t W = (in->n_images + 63) / 64;
   constexpr uint32_t kListMax = 12;
-  std::vector<uint32_t> set_size(small_sets ? 0 : N, 1);
-  std::vector<int32_t> set_slot(small_sets ? 0 : N, -1);   // index into lists (size <= kListMax) or bitsets (above)
   std::vector<uint16_t> lists;                               // kListMax entries per slot
   std::vector<uint64_t> bitsets;                             // W words per slot
   std::vector<int32_t> free_lists;
   if (small_sets)
     for (uint32_t v = 0; v < N; ++v) mask[v] = 1ull << hs->node_image[v];
   auto set_has = [&](uint32_t r, uint16_t img) -> bool {
-    const uint32_t sz = set_size[r];
+    const uint32_t sz = uf[r].size;
     if (sz == 1) return (uint16_t)hs->node_image[r] == img;
     if (sz <= kListMax) {
-      const uint16_t* l = &lists[(size_t)set_slot[r] * kListMax];
+      const uint16_t* l = &lists[(size_t)uf[r].slot * kListMax];
       for (uint32_t i = 0; i < sz; ++i)
         if (l[i] == img) return true;
       return false;
     }
-    return (bitsets[(size_t)set_slot[r] * W + (img >> 6)] >> (img & 63)) & 1ull;
+    return (bitsets[(size_t)uf[r].slot * W + (img >> 6)] >> (img & 63)) & 1ull;
   };
   // visit the images of root r
   auto for_each_image = [&](uint32_t r, auto&& fn) {
-    const uint32_t sz = set_size[r];
+    const uint32_t sz = uf[r].size;
     if (sz == 1) {
       fn((uint16_t)hs->node_image[r]);
     } else if (sz <= kListMax) {
-      const uint16_t* l = &lists[(size_t)set_slot[r] * kListMax];
+      const uint16_t* l = &lists[(size_t)uf[r].slot * kListMax];
       for (uint32_t i = 0; i < sz; ++i) fn(l[i]);
     } else {
-      const uint64_t* b = &bitsets[(size_t)set_slot[r] * W];
+      const uint64_t* b = &bitsets[(size_t)uf[r].slot * W];
       for (uint32_t w = 0; w < W; ++w)
         for (uint64_t m = b[w]; m; m &= m - 1) fn((uint16_t)(64 * w + __builtin_ctzll(m)));
     }
   };
   auto sets_clash = [&](uint32_t a, uint32_t b) -> bool {  // a = the smaller set
-    if (set_size[a] > kListMax && set_size[b] > kListMax) {
-      const uint64_t* x = &bitsets[(size_t)set_slot[a] * W];
-      const uint64_t* y = &bitsets[(size_t)set_slot[b] * W];
+    if (uf[a].size > kListMax && uf[b].size > kListMax) {
+      const uint64_t* x = &bitsets[(size_t)uf[a].slot * W];
+      const uint64_t* y = &bitsets[(size_t)uf[b].slot * W];
       for (uint32_t w = 0; w < W; ++w)
         if (x[w] & y[w]) return true;
       return false;
@@ -495,9 +511,9 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   };
   // dst <- dst U src (disjoint), src released
   auto absorb = [&](uint32_t dst, uint32_t src) {
-    const uint32_t new_size = set_size[dst] + set_size[src];
+    const uint32_t new_size = uf[dst].size + uf[src].size;
     if (new_size <= kListMax) {
-      if (set_slot[dst] < 0) {  // singleton -> list
+      if (uf[dst].slot < 0) {  // singleton -> list
         int32_t sl;
         if (!free_lists.empty()) {
           sl = free_lists.back();
@@ -507,68 +523,81 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
           lists.resize(lists.size() + kListMax);
         }
         lists[(size_t)sl * kListMax] = (uint16_t)hs->node_image[dst];
-        set_slot[dst] = sl;
+        uf[dst].slot = sl;
       }
-      uint16_t* l = &lists[(size_t)set_slot[dst] * kListMax];
-      uint32_t n = set_size[dst];
+      uint16_t* l = &lists[(size_t)uf[dst].slot * kListMax];
+      uint32_t n = uf[dst].size;
       for_each_image(src, [&](uint16_t img) { l[n++] = img; });
     } else {
-      if (set_size[dst] <= kListMax) {  // singleton / list -> bitset
+      if (uf[dst].size <= kListMax) {  // singleton / list -> bitset
         const int32_t sl = (int32_t)(bitsets.size() / W);
         bitsets.resize(bitsets.size() + W, 0);
         uint64_t* b = &bitsets[(size_t)sl * W];
         for_each_image(dst, [&](uint16_t img) { b[img >> 6] |= 1ull << (img & 63); });
-        if (set_slot[dst] >= 0) free_lists.push_back(set_slot[dst]);
-        set_slot[dst] = sl;
+        if (uf[dst].slot >= 0) free_lists.push_back(uf[dst].slot);
+        uf[dst].slot = sl;
       }
-      uint64_t* b = &bitsets[(size_t)set_slot[dst] * W];
-      if (set_size[src] > kListMax) {
-        const uint64_t* c = &bitsets[(size_t)set_slot[src] * W];
+      uint64_t* b = &bitsets[(size_t)uf[dst].slot * W];
+      if (uf[src].size > kListMax) {
+        const uint64_t* c = &bitsets[(size_t)uf[src].slot * W];
         for (uint32_t w = 0; w < W; ++w) b[w] |= c[w];
       } else {
         for_each_image(src, [&](uint16_t img) { b[img >> 6] |= 1ull << (img & 63); });
       }
     }
-    if (set_slot[src] >= 0 && set_size[src] <= kListMax) free_lists.push_back(set_slot[src]);
-    set_size[dst] = new_size;
-    set_size[src] = 0;
-    set_slot[src] = -1;
+    if (uf[src].slot >= 0 && uf[src].size <= kListMax) free_lists.push_back(uf[src].slot);
+    uf[dst].size = new_size;
+    uf[src].size = 0;
+    uf[src].slot = -1;
   };
   auto find = [&](uint32_t x) {
     uint32_t r = x;
-    while (parent[r] != -1) r = (uint32_t)parent[r];
-    while (parent[x] != -1) {  // path compression (solve.cc:74-76)
-      const uint32_t nx = (uint32_t)parent[x];
-      parent[x] = (int32_t)r;
+    while (uf[r].parent != -1) r = (uint32_t)uf[r].parent;
+    while (uf[x].parent != -1) {  // path compression (solve.cc:74-76)
+      const uint32_t nx = (uint32_t)uf[x].parent;
+      uf[x].parent = (int32_t)r;
       x = nx;
     }
     return r;
   };
+  // the loop is a chain of dependent random reads (order -> n1/n2 -> parent -> set): the lines of the
+  // edges to come are requested ahead, in two stages (node ids 16 edges ahead, their parents 8 ahead)
+  constexpr uint64_t kAheadIds = 16, kAheadParents = 8;
   for (uint64_t oi = M; oi-- > 0;) {
+    if (oi >= kAheadIds) {
+      const uint32_t ka = order[oi - kAheadIds];
+      __builtin_prefetch(&n1[ka]);
+      __builtin_prefetch(&n2[ka]);
+    }
+    if (oi >= kAheadParents) {
+      const uint32_t kb = order[oi - kAheadParents];
+      __builtin_prefetch(&uf[n1[kb]].parent);
+      __builtin_prefetch(&uf[n2[kb]].parent);
+    }
     const uint32_t k = order[oi];
     const uint32_t r1 = find(n1[k]), r2 = find(n2[k]);
     if (r1 == r2) continue;
     if (small_sets) {
       if (mask[r1] & mask[r2]) continue;  // set_intersection non-empty (solve.cc:507-511)
       if (__builtin_popcountll(mask[r1]) < __builtin_popcountll(mask[r2])) {  // solve.cc:513-521
-        parent[r1] = (int32_t)r2;
+        uf[r1].parent = (int32_t)r2;
         mask[r2] |= mask[r1];
         mask[r1] = 0;
       } else {
-        parent[r2] = (int32_t)r1;
+        uf[r2].parent = (int32_t)r1;
         mask[r1] |= mask[r2];
         mask[r2] = 0;
       }
       continue;
     }
     // std::set_intersection non-empty (solve.cc:507-511); smaller set under larger, tie: root2 under root1 (:513-521)
-    const bool r1_smaller = set_size[r1] < set_size[r2];
+    const bool r1_smaller = uf[r1].size < uf[r2].size;
     if (sets_clash(r1_smaller ? r1 : r2, r1_smaller ? r2 : r1)) continue;
     if (r1_smaller) {
-      parent[r1] = (int32_t)r2;
+      uf[r1].parent = (int32_t)r2;
       absorb(r2, r1);
     } else {
-      parent[r2] = (int32_t)r1;
+      uf[r2].parent = (int32_t)r1;
       absorb(r1, r2);
     }
   }
@@ -576,9 +605,9 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   hs->track.assign(N, 0);
   uint32_t T = 0;
   for (uint32_t v = 0; v < N; ++v)
-    if (parent[v] == -1) hs->track[v] = T++;
+    if (uf[v].parent == -1) hs->track[v] = T++;
   for (uint32_t v = 0; v < N; ++v)
-    if (parent[v] != -1) hs->track[v] = hs->track[find(v)];
+    if (uf[v].parent != -1) hs->track[v] = hs->track[find(v)];
   hs->T = T;
   std::vector<uint32_t> nodes_in_track(T, 0);
   for (uint32_t v = 0; v < N; ++v) ++nodes_in_track[hs->track[v]];
