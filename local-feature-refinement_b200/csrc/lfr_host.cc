@@ -613,6 +613,10 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   for (uint32_t v = 0; v < N; ++v) ++nodes_in_track[hs->track[v]];
   S.max_track_size = *std::max_element(nodes_in_track.begin(), nodes_in_track.end());
   const double t_ids = ms_since(t_tracks);
+  // track of every edge's destination, gathered once: the root scores and the two meta-graph sweeps
+  // below then stream (cdst is not needed any more)
+  for (size_t e = 0; e < cdst.size(); ++e) cdst[e] = hs->track[cdst[e]];
+  const std::vector<uint32_t>& tdst = cdst;
   // ---- H3: roots (solve.cc:552-582) -----------------------------------------------------------
   hs->is_root.assign(N, 0);
   {
@@ -622,7 +626,7 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     for (uint32_t v = 0; v < N; ++v) {
       double score = 0.0;
       for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e)
-        if (hs->track[v] == hs->track[cdst[e]]) score += (double)csim[e];
+        if (hs->track[v] == tdst[e]) score += (double)csim[e];
       const uint32_t t = hs->track[v];
       if (!has[t] || score > best_score[t] || (score == best_score[t] && v > best_node[t])) {
         has[t] = 1;
@@ -643,14 +647,14 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
   {
     uint64_t n_inter = 0;
     for (uint32_t v = 0; v < N; ++v)
-      for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e) n_inter += hs->track[v] != hs->track[cdst[e]];
+      for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e) n_inter += hs->track[v] != tdst[e];
     FlatMap slot((size_t)n_inter);
     std::vector<uint64_t> keys;
     std::vector<double> sums;
     for (uint32_t v = 0; v < N; ++v) {
       const uint32_t ts = hs->track[v];
       for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e) {
-        const uint32_t tt = hs->track[cdst[e]];
+        const uint32_t tt = tdst[e];
         if (ts == tt) continue;
         const uint64_t key = (uint64_t)ts * T + tt;
         bool fresh;
