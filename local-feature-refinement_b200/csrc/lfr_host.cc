@@ -648,36 +648,44 @@ int lfr_host_stage_create(const lfr_host_input* in, lfr_host_stage** out, lfr_ho
     uint64_t n_inter = 0;
     for (uint32_t v = 0; v < N; ++v)
       for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e) n_inter += hs->track[v] != tdst[e];
-    FlatMap slot((size_t)n_inter);
-    std::vector<uint64_t> keys;
-    std::vector<double> sums;
-    for (uint32_t v = 0; v < N; ++v) {
-      const uint32_t ts = hs->track[v];
-      for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e) {
-        const uint32_t tt = tdst[e];
-        if (ts == tt) continue;
-        const uint64_t key = (uint64_t)ts * T + tt;
-        bool fresh;
-        const size_t sl = slot.find_or_insert(key, &fresh);
-        if (fresh) {
-          slot.vals[sl] = (uint32_t)keys.size();
-          keys.push_back(key);
-          sums.push_back((double)csim[e]);
-        } else {
-          sums[slot.vals[sl]] += (double)csim[e];  // accumulation in node / out-edge order
+    // the inter-track edges in traversal order, then a STABLE radix sort by (source track, destination
+    // track): equal keys stay in traversal order, so each meta-edge weight is the same left-to-right
+    // double sum a map keyed by the pair accumulates (solve.cc:262-283) — without a hash probe per edge
+    std::vector<uint64_t> ikey(n_inter);
+    std::vector<float> isim(n_inter);
+    {
+      size_t w = 0;
+      for (uint32_t v = 0; v < N; ++v) {
+        const uint32_t ts = hs->track[v];
+        for (uint32_t e = hs->row_ptr[v]; e < hs->row_ptr[v + 1]; ++e) {
+          const uint32_t tt = tdst[e];
+          if (ts == tt) continue;
+          ikey[w] = (uint64_t)ts * T + tt;
+          isim[w] = csim[e];
+          ++w;
         }
       }
     }
-    std::vector<uint32_t> idx(keys.size());
-    std::iota(idx.begin(), idx.end(), 0u);
-    std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
-    ma.resize(keys.size());
-    mb.resize(keys.size());
-    wsum.resize(keys.size());
-    for (size_t i = 0; i < idx.size(); ++i) {
-      ma[i] = (uint32_t)(keys[idx[i]] / T);
-      mb[i] = (uint32_t)(keys[idx[i]] % T);
-      wsum[i] = sums[idx[i]];
+    std::vector<uint32_t> oa(n_inter), ob(n_inter);
+    std::iota(oa.begin(), oa.end(), 0u);
+    int key_bits = 1;
+    while (key_bits < 64 && ((uint64_t)T * T >> key_bits)) ++key_bits;
+    for (int shift = 0; shift < key_bits; shift += 11) {
+      uint32_t hist[2049] = {0};
+      for (size_t i = 0; i < n_inter; ++i) ++hist[((ikey[i] >> shift) & 2047u) + 1];
+      for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
+      for (size_t i = 0; i < n_inter; ++i) ob[hist[(ikey[oa[i]] >> shift) & 2047u]++] = oa[i];
+      oa.swap(ob);
+    }
+    for (size_t i = 0; i < n_inter;) {
+      const uint64_t key = ikey[oa[i]];
+      double sum = (double)isim[oa[i]];
+      size_t j = i + 1;
+      for (; j < n_inter && ikey[oa[j]] == key; ++j) sum += (double)isim[oa[j]];
+      ma.push_back((uint32_t)(key / T));
+      mb.push_back((uint32_t)(key % T));
+      wsum.push_back(sum);
+      i = j;
     }
   }
   const double t_meta = ms_since(t_cut);
