@@ -135,3 +135,24 @@ def test_gpu_native_executable_reproduces_the_reference_binarys_solution_file(pr
         for (na, fa, ia, dia, dja), (nb, fb, ib, dib, djb) in zip(a, b):
             assert fa == fb and np.array_equal(ia, ib)
             assert np.abs(dia - dib).max() <= 1e-4 / 16 and np.abs(dja - djb).max() <= 1e-4 / 16
+
+
+def test_image_names_are_bytes_to_both_hosts(checker_exe, oracle, tmp_path):
+    """Names with spaces, non-ASCII characters and invalid UTF-8 travel through unchanged (the reference
+    treats them as std::string); banned images are matched on the same bytes."""
+    ms = synth.generate("cfg1", seed=5)
+    odd = ["im age 0.png", "bild-äöü.jpg", b"raw-\xff\xfe.png".decode("utf-8", errors="surrogateescape")]
+    ms.image_names = odd[:len(ms.image_names)] + ms.image_names[len(odd):]
+    data = wire.encode_matching_file(ms)
+    m, o = tmp_path / "m.pb", tmp_path / "o.pb"
+    m.write_bytes(data)
+    r = subprocess.run([checker_exe, "--matches_file", str(m), "--output_file", str(o)], capture_output=True)
+    assert r.returncode == 0, r.stderr
+    mine, _, _, _ = oracle_pipeline(oracle, data)
+    assert o.read_bytes() == mine
+    # ban the non-ASCII one (argv carries the same bytes)
+    o2 = tmp_path / "o2.pb"
+    r = subprocess.run([checker_exe, "--matches_file", str(m), "--output_file", str(o2), "--banned_images", odd[1]], capture_output=True)
+    assert r.returncode == 0, r.stderr
+    mine2, _, _, _ = oracle_pipeline(oracle, data, banned=[odd[1]])
+    assert o2.read_bytes() == mine2 and mine2 != mine
