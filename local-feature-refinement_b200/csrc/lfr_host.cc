@@ -185,6 +185,21 @@ std::vector<uint32_t> connected_components(uint32_t n, const std::vector<uint32_
 void cut_step(const std::vector<lfr::CutEdge>& edges, const std::vector<uint32_t>& node_weight, uint32_t max_weight,
               lfr::CutWorkspace& W, std::vector<uint8_t>& covered, std::vector<std::vector<uint32_t>>* groups,
               std::vector<lfr::CutEdge> (&sub)[2]) {
+  // a third of all sub-problems are two tracks joined by (parallel) edges: whatever their weights, each
+  // side of the cut is one node with no edge inside — two singleton groups (solve.cc:205-211 / :240-246)
+  {
+    const uint32_t a = edges[0].a, b = edges[0].b;
+    bool two_nodes = a != b;
+    for (size_t i = 1; two_nodes && i < edges.size(); ++i)
+      two_nodes = (edges[i].a == a && edges[i].b == b) || (edges[i].a == b && edges[i].b == a);
+    if (two_nodes) {
+      sub[0].clear();
+      sub[1].clear();
+      groups->push_back(std::vector<uint32_t>(1, a));
+      groups->push_back(std::vector<uint32_t>(1, b));
+      return;
+    }
+  }
   lfr::two_way_cut(edges.data(), edges.size(), W);
   const uint32_t n = (uint32_t)W.nodes.size();
   for (int s = 0; s < 2; ++s) {
