@@ -136,10 +136,14 @@ def encode_matching_file(ms: MatchSet, pair_lo: int = 0, pair_hi: Optional[int] 
             np.ascontiguousarray(ms.sim, np.float32), np.ascontiguousarray(ms.disp1, np.float32),
             np.ascontiguousarray(ms.disp2, np.float32)]
     ptrs = [x.ctypes.data for x in arrs]
-    need = L.lfr_wire_encode_matches(n, *ptrs, None, 0)
-    out = np.zeros(max(int(need), 1), np.uint8)
-    got = L.lfr_wire_encode_matches(n, *ptrs, out.ctypes.data, int(need))
-    assert got == need
+    # one call into a buffer of the largest possible size (a match is at most 18 x 12 displacement bytes +
+    # 17 of scalars + 3 of framing; a pair two names, two facts and framing) instead of a sizing call first
+    n_m = int(pair_ptr[-1] - pair_ptr[0]) if n else 0
+    longest = int(np.max(off[1:] - off[:-1])) if len(ms.image_names) else 0
+    cap = 240 * n_m + (2 * longest + 64) * n + 16
+    out = np.empty(cap, np.uint8)
+    need = int(L.lfr_wire_encode_matches(n, *ptrs, out.ctypes.data, cap))
+    assert 0 <= need <= cap
     return out[:need].tobytes()
 
 
