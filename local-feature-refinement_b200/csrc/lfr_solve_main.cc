@@ -18,12 +18,17 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
 #include <fstream>
 #include <map>
 #include <set>
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/lfr.h"
 #include "../../include/lfr_host.h"
@@ -128,19 +133,44 @@ bool file_exists(const std::string& path) {
   return f.good();
 }
 
-bool read_file(const std::string& path, std::vector<uint8_t>* out) {
-  std::ifstream f(path, std::ios::binary | std::ios::ate);
-  if (!f) return false;
-  const std::streamsize n = f.tellg();
-  f.seekg(0);
-  out->resize((size_t)n);
-  if (n && !f.read(reinterpret_cast<char*>(out->data()), n)) return false;
-  return true;
-}
+// A file mapped read-only (a Madrid-scale MatchingFile is several GB: no second copy of it in memory).
+struct FileImage {
+  const uint8_t* p = nullptr;
+  size_t n = 0;
+  bool open(const std::string& path) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+      ::close(fd);
+      return false;
+    }
+    n = (size_t)st.st_size;
+    if (n) {
+      void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+      ::close(fd);
+      if (m == MAP_FAILED) {
+        n = 0;
+        return false;
+      }
+      p = static_cast<const uint8_t*>(m);
+    } else {
+      ::close(fd);
+    }
+    return true;
+  }
+  void release() {
+    if (p) munmap(const_cast<uint8_t*>(p), n);
+    p = nullptr;
+    n = 0;
+  }
+  const uint8_t* data() const { return p; }
+  size_t size() const { return n; }
+};
 
 // One decoded MatchingFile part, image names still as byte ranges of its buffer.
 struct Part {
-  std::vector<uint8_t> buf;
+  FileImage buf;
   uint64_t P = 0, M = 0;
   std::vector<uint64_t> pair_ptr, n1_off, n2_off;
   std::vector<uint32_t> n1_len, n2_len, feat1, feat2;
@@ -207,7 +237,7 @@ int main(int argc, char** argv) {
   std::vector<Part> parts(files.size());
   for (size_t i = 0; i < files.size(); ++i) {
     Part& pt = parts[i];
-    bool ok = read_file(files[i], &pt.buf);
+    bool ok = pt.buf.open(files[i]);
     if (ok) ok = lfr_wire_scan_matches(pt.buf.data(), pt.buf.size(), &pt.P, &pt.M) == LFR_OK;
     if (ok) {
       pt.pair_ptr.resize(pt.P + 1);
@@ -274,7 +304,7 @@ int main(int argc, char** argv) {
       }
       p0 += pt.P;
       m0 += pt.M;
-      std::vector<uint8_t>().swap(pt.buf);  // the file image (7 GB at Madrid scale) is not needed past the names
+      pt.buf.release();  // the file image (several GB at Madrid scale) is not needed past the names
       if (cat) {
         std::vector<uint32_t>().swap(pt.feat1);
         std::vector<uint32_t>().swap(pt.feat2);
